@@ -1,0 +1,123 @@
+/*
+ * w3_oracle.h — CPU restatement of weath3rb0i's predict→update→code path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product:
+ * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * `--impl reference` legs may load this library, and only as the checker or as
+ * the reported CPU baseline.  The product (weath3rb0i_b200/) never links or
+ * calls it and has no CPU fallback.
+ *
+ * Parity status:
+ *   - arithmetic coder + bit I/O: PINNED by the reference's own known-answer
+ *     tests (src/entropy_coding/arithmetic_coder_tests.rs:44-161,
+ *     src/entropy_coding/io.rs:107-227), replayed in tests/test_oracle_kats.py.
+ *   - OrderNEntropy / Counter / ACHistory / StationaryModel / header: the
+ *     reference holds NO test or golden vector for these and no Rust toolchain
+ *     exists in this image (oracle/_ref cannot be built) — "parity unpinned"
+ *     by reference fixtures.  Mitigation: this C restatement and the
+ *     independent Python restatement (oracle/w3_oracle.py) must agree
+ *     byte-for-byte (tests/test_oracle_cross.py) and every function below
+ *     cites the reference file:line it follows.
+ *
+ * All citations are relative to /root/reference/.
+ */
+#ifndef W3_ORACLE_H
+#define W3_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define W3O_OK 0
+#define W3O_E_CAP (-1) /* output buffer too small */
+#define W3O_E_ARG (-2) /* bad argument */
+#define W3O_E_MAGIC (-3) /* header magic mismatch (src/main.rs:123-124) */
+
+/* ---- models ------------------------------------------------------------ */
+
+/* Counter::p — src/models/counter.rs:13-18 */
+uint16_t w3o_counter_p(uint16_t c0, uint16_t c1);
+/* Counter::update — src/models/counter.rs:20-26; c = {c0, c1} in place */
+void w3o_counter_update(uint16_t c[2], int bit);
+
+/* StationaryModel::for_book1 table — src/models/ac_hash/stationary.rs:40-42 */
+extern const uint16_t W3O_BOOK1_TABLE[8];
+
+/* ACHistory::hash with max_bits = 8 and the book1 StationaryModel —
+ * src/history/ac_history.rs:28-46 (+ EntropyWriter 50-88,
+ * StationaryModel::{align,predict} src/models/ac_hash/stationary.rs:49-57).
+ * `steps` (optional) receives the number of history bits consumed when the
+ * 8-bit sink became full, i.e. the hash depends on the low `steps` bits only
+ * (65 if the sink never filled within the 64 bits). */
+uint32_t w3o_achash(uint64_t bits, uint64_t pos, int *steps);
+/* same, arbitrary table / max_bits (for StationaryModel::from_table variants) */
+uint32_t w3o_achash_ex(uint64_t bits, uint64_t pos, const uint16_t table[8],
+                       int max_bits, int *steps);
+
+/* ---- bit I/O (src/entropy_coding/io.rs) -------------------------------- */
+
+typedef struct w3o_writer w3o_writer; /* ACWriter io.rs:52-101 */
+w3o_writer *w3o_writer_new(uint8_t *buf, size_t cap);
+void w3o_writer_free(w3o_writer *w);
+void w3o_writer_write_bit(w3o_writer *w, int bit); /* io.rs:70-89 */
+void w3o_writer_inc_parity(w3o_writer *w);         /* io.rs:66-68 */
+void w3o_writer_flush(w3o_writer *w, uint32_t state); /* io.rs:91-100 */
+size_t w3o_writer_len(const w3o_writer *w);  /* bytes produced so far */
+int w3o_writer_overflowed(const w3o_writer *w);
+
+typedef struct w3o_reader w3o_reader; /* ACReader io.rs:7-49 */
+w3o_reader *w3o_reader_new(const uint8_t *buf, size_t n);
+void w3o_reader_free(w3o_reader *r);
+int w3o_reader_read_bit(w3o_reader *r);      /* io.rs:31-38, 0 past EOF */
+uint32_t w3o_reader_read_u32(w3o_reader *r); /* io.rs:40-48, zero-padded */
+
+/* ---- arithmetic coder with caller-supplied probabilities ---------------
+ * Mirrors the helper pair in src/entropy_coding/arithmetic_coder_tests.rs:8-42:
+ * `in` is read MSB-first one bit per probability. */
+int w3o_ac_encode_probs(const uint8_t *in, size_t n_in, const uint16_t *probs,
+                        size_t n_probs, uint8_t *out, size_t cap,
+                        size_t *out_len);
+/* decodes n_probs bits, packs them MSB-first into out (ceil(n/8) bytes) */
+int w3o_ac_decode_probs(const uint8_t *in, size_t n_in, const uint16_t *probs,
+                        size_t n_probs, uint8_t *out, size_t cap);
+
+/* ---- the codec path (src/main.rs:89-152) ------------------------------- */
+
+/* Stream bytes the reference writes AFTER its 12-byte header for a file equal
+ * to in[0..n): compress loop main.rs:99-111 with init_model main.rs:146-152.
+ * *out_len receives the full stream length even when it exceeds cap (then
+ * the return is W3O_E_CAP and only cap bytes were stored). */
+int w3o_compress_block(const uint8_t *in, size_t n, uint8_t *out, size_t cap,
+                       size_t *out_len);
+/* decompress loop main.rs:127-140 over one stream; bits past n_in read as 0 */
+int w3o_decompress_block(const uint8_t *in, size_t n_in, uint8_t *out,
+                         size_t n_out);
+
+/* Whole reference file: "w30i" + u64 BE length + stream (main.rs:14-15,95-96) */
+int w3o_compress_file(const uint8_t *in, size_t n, uint8_t *out, size_t cap,
+                      size_t *out_len);
+int w3o_decompress_file(const uint8_t *in, size_t n_in, uint8_t *out,
+                        size_t cap, size_t *out_len);
+
+/* Context trace: ctx used to code each of the 8*n bits (for kernel debugging
+ * and the Appendix-B trace check). ctx_out has 8*n entries. */
+void w3o_ctx_trace(const uint8_t *in, size_t n, uint16_t *ctx_out);
+
+/* ---- multi-threaded CPU baseline (bench only) --------------------------
+ * Runs w3o_compress_block / w3o_decompress_block over `n_blocks` independent
+ * blocks with `n_threads` std threads, one block per thread at a time
+ * (BASELINE.md §3).  Offsets/lengths arrays have n_blocks entries. */
+int w3o_compress_blocks_mt(const uint8_t *in, size_t n, size_t block_size,
+                           uint8_t *out, size_t out_stride, uint32_t *out_lens,
+                           int n_threads);
+int w3o_decompress_blocks_mt(const uint8_t *in, size_t in_stride,
+                             const uint32_t *in_lens, uint8_t *out, size_t n,
+                             size_t block_size, int n_threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
