@@ -15,6 +15,9 @@ GOLDEN = 0x9E3779B97F4A7C15
 CHUNK = 65536
 VOCAB = 8192
 M64 = (1 << 64) - 1
+# frozen digests of the first 1 MiB / 64 MiB of the stream (also in BASELINE.md)
+SHA256_1MIB = "10b1957134262774dae2cd90f01ed794b00e3a53a1ebc4fe00bc77040590b290"
+SHA256_64MIB = "3ef7833dde9d2047ca41de15a63ddbc41f64238b7933fe0c4b3ee23d2fc9bca0"
 
 FUNCTION_WORDS = (
     "the of and to a in that is was he for it with as his on be at by i this had "

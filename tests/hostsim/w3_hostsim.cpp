@@ -1,0 +1,139 @@
+/*
+ * w3_hostsim.cpp — TEST SUPPORT ONLY.  Compiles weath3rb0i_b200/csrc/w3_core.cuh
+ * (the statements the kernels execute) with g++ so that the closed-form
+ * renormalisation, the threshold-table hash, the float-estimate Counter::p and
+ * the word writer can be compared with the oracle on the CPU.  Nothing in the
+ * product loads this library.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "../../weath3rb0i_b200/csrc/w3_core.cuh"
+
+extern "C" {
+
+int hs_tab_size(void) { return (int)sizeof(w3_hashtab); }
+
+int hs_build_table(const uint16_t *table, int max_bits, w3_hashtab *tab) {
+  memset(tab, 0, sizeof *tab);
+  for (int i = 0; i < 8; i++) tab->table[i] = table[i];
+  tab->max_bits = (uint16_t)max_bits;
+  for (uint32_t a = 0; a < 8; a++)
+    for (uint32_t j = 0; j < 256; j++) w3_build_thr(tab, a, j);
+  for (uint32_t a = 0; a < 8; a++) {
+    for (uint32_t c = 0; c < W3_NCELL; c++) w3_build_cell(tab, a, c);
+    for (uint32_t r = 0; r < 256; r++) w3_build_rval(tab, a, r);
+  }
+  return tab->bad;
+}
+
+uint32_t hs_hash_exact(uint64_t bits, uint32_t pos, const uint16_t *table, int max_bits,
+                       int *idx) {
+  w3_hash_result r = w3_achash_exact(bits, pos, table, max_bits);
+  if (idx) *idx = r.idx;
+  return r.hash;
+}
+
+/* table lookup with the exact fallback, as the kernels do it */
+uint32_t hs_hash(const w3_hashtab *tab, uint64_t bits, uint32_t pos, int *slow) {
+  uint32_t h = w3_hash_lookup(w3_key_of_history(bits), pos & 7u, &tab->thr[0][0],
+                              &tab->cell[0][0], &tab->rval[0][0]);
+  if (slow) *slow = h == 0xFFFFFFFFu;
+  if (h == 0xFFFFFFFFu) h = w3_achash_exact(bits, pos, tab->table, tab->max_bits).hash;
+  return h;
+}
+
+/* number of thresholds compared for this key (cell occupancy statistics) */
+uint32_t hs_cell_count(const w3_hashtab *tab, uint64_t bits, uint32_t pos) {
+  uint64_t key = w3_key_of_history(bits);
+  return tab->cell[pos & 7u][key >> (64 - W3_PB)] >> 8;
+}
+
+uint32_t hs_counter_p(uint32_t c0, uint32_t c1) { return w3_counter_p(c0, c1); }
+/* returns number of mismatches of the float-estimate p against the u64 form */
+uint64_t hs_counter_p_sweep(uint32_t c0_lo, uint32_t c0_hi, uint32_t step) {
+  uint64_t bad = 0;
+  for (uint32_t c0 = c0_lo; c0 < c0_hi; c0 += step)
+    for (uint32_t c1 = 0; c1 <= 65534; c1++) bad += w3_counter_p(c0, c1) != w3_counter_p_u64(c0, c1);
+  return bad;
+}
+uint32_t hs_counter_update(uint32_t slot, uint32_t bit) { return w3_counter_update(slot, bit); }
+
+/* scalar encode of one block, built only from w3_core.cuh statements */
+int hs_compress_block(const w3_hashtab *tab, const uint8_t *in, size_t n, uint8_t *out, size_t cap,
+                      size_t *out_len) {
+  std::vector<uint32_t> stats(W3_NCTX, 0u);
+  uint32_t x1 = 0, x2 = 0xFFFFFFFFu, ctx = 0;
+  uint64_t hist = 0;
+  w3_writer w;
+  w3_writer_init(w);
+  auto store = [&](uint32_t idx, uint32_t v) {
+    for (int b = 0; b < 4; b++)
+      if ((size_t)idx * 4 + b < cap) out[(size_t)idx * 4 + b] = (uint8_t)(v >> (24 - 8 * b));
+  };
+  uint64_t t = 0;
+  for (size_t i = 0; i < n; i++)
+    for (int kbit = 7; kbit >= 0; kbit--) {
+      uint32_t bit = (in[i] >> kbit) & 1u;
+      uint32_t slot = stats[ctx];
+      uint32_t p = w3_counter_p(slot & 0xFFFFu, slot >> 16);
+      stats[ctx] = w3_counter_update(slot, bit);
+      hist = (hist << 1) | bit;
+      t++;
+      ctx = (hs_hash(tab, hist, (uint32_t)t, nullptr) << 3) | (uint32_t)(t & 7u);
+      w3_ac_narrow(x1, x2, bit, w3_prob32(p));
+      uint32_t pre = x1;
+      int s, k;
+      w3_ac_renorm(x1, x2, s, k);
+      w3_writer_step(w, pre, s, k, store);
+    }
+  uint32_t tail, tb;
+  uint64_t len = w3_writer_flush(w, x2, tail, tb, store);
+  for (uint32_t b = 0; b < tb; b++)
+    if ((size_t)w.words * 4 + b < cap) out[(size_t)w.words * 4 + b] = (uint8_t)(tail >> (24 - 8 * b));
+  *out_len = (size_t)len;
+  return len > cap ? -1 : 0;
+}
+
+/* scalar decode of one block stream */
+int hs_decompress_block(const w3_hashtab *tab, const uint8_t *in, size_t n_in, uint8_t *out,
+                        size_t n_out) {
+  std::vector<uint32_t> stats(W3_NCTX, 0u);
+  uint32_t x1 = 0, x2 = 0xFFFFFFFFu, ctx = 0;
+  uint64_t hist = 0, t = 0;
+  size_t bitpos = 0;
+  auto take = [&](int c) -> uint32_t {
+    uint32_t v = 0;
+    for (int i = 0; i < c; i++, bitpos++) {
+      size_t by = bitpos >> 3;
+      uint32_t b = by < n_in ? (in[by] >> (7 - (bitpos & 7))) & 1u : 0u;
+      v = (v << 1) | b;
+    }
+    return v;
+  };
+  uint32_t x = take(16) << 16;
+  x |= take(16);
+  for (size_t i = 0; i < n_out; i++) {
+    uint32_t byte = 0;
+    for (int kbit = 0; kbit < 8; kbit++) {
+      uint32_t slot = stats[ctx];
+      uint32_t P = w3_prob32(w3_counter_p(slot & 0xFFFFu, slot >> 16));
+      uint32_t xmid = x1 + w3_umulhi(x2 - x1, P);
+      uint32_t bit = x <= xmid ? 1u : 0u;
+      if (bit) x2 = xmid; else x1 = xmid + 1;
+      int s, k;
+      int nsh = w3_ac_renorm(x1, x2, s, k);
+      if (nsh) x = ((x << nsh) | take(nsh)) ^ (k ? 0x80000000u : 0u);
+      stats[ctx] = w3_counter_update(slot, bit);
+      hist = (hist << 1) | bit;
+      t++;
+      ctx = (hs_hash(tab, hist, (uint32_t)t, nullptr) << 3) | (uint32_t)(t & 7u);
+      byte = (byte << 1) | bit;
+    }
+    out[i] = (uint8_t)byte;
+  }
+  return 0;
+}
+
+} /* extern "C" */

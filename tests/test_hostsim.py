@@ -1,0 +1,117 @@
+"""w3_core.cuh (the statements the CUDA kernels execute) compiled for the CPU
+and compared with the oracle: closed-form renormalisation, threshold-table
+hash, float-estimate Counter::p, word writer.  No GPU needed."""
+import random
+
+import pytest
+
+from corpus import w3_corpus
+from tests._libs import BOOK1, ENWIK7, HostSim
+
+
+def test_table_builds_monotone(libs):
+    assert libs.hostsim.bad == 0
+    thr, sing = libs.hostsim.thresholds()
+    for a in range(8):
+        assert thr[a][:255] == sorted(thr[a][:255])
+        assert thr[a][255] == (1 << 64) - 1
+
+
+def test_hash_table_equals_oracle_random(libs):
+    rnd = random.Random(11)
+    for i in range(60000):
+        bits = rnd.getrandbits(64)
+        if i % 3 == 0:
+            bits &= (1 << rnd.randrange(1, 64)) - 1
+        pos = rnd.randrange(0, 1 << 24)
+        assert libs.hostsim.hash(bits, pos)[0] == libs.oracle.achash(bits, pos)[0]
+
+
+def _rev64(v):
+    return int(f"{v:064b}"[::-1], 2)
+
+
+def test_hash_table_at_every_threshold(libs):
+    """Keys at, just below and just above each of the 8 x 255 thresholds —
+    including the singular keys, which must take the literal-loop fallback."""
+    thr, sing = libs.hostsim.thresholds()
+    n_sing = 0
+    for a in range(8):
+        for j in range(255):
+            for key in (thr[a][j] - 1, thr[a][j], thr[a][j] + 1):
+                if not 0 <= key < 1 << 64:
+                    continue
+                bits = _rev64(key)
+                got, slow = libs.hostsim.hash(bits, a)
+                assert got == libs.oracle.achash(bits, a)[0], (a, j, hex(key))
+                if key == thr[a][j]:
+                    assert slow
+            if sing[a][j]:
+                n_sing += 1
+                _, idx = libs.hostsim.hash_exact(_rev64(thr[a][j]), a)
+                assert idx < 8
+    assert n_sing > 0
+
+
+def test_hash_table_other_model(libs):
+    hs = HostSim(ENWIK7, 8)
+    assert hs.bad == 0
+    rnd = random.Random(5)
+    for _ in range(20000):
+        bits, pos = rnd.getrandbits(64), rnd.randrange(64)
+        assert hs.hash(bits, pos)[0] == libs.oracle.achash(bits, pos, ENWIK7, 8)[0]
+
+
+def test_counter_p_estimate_is_exact(libs):
+    lib = libs.hostsim.lib
+    assert lib.hs_counter_p_sweep(0, 2048, 1) == 0
+    assert lib.hs_counter_p_sweep(2048, 65535, 61) == 0
+    assert lib.hs_counter_p_sweep(65400, 65535, 1) == 0
+
+
+def test_counter_update(libs):
+    import ctypes as C
+
+    rnd = random.Random(3)
+    for _ in range(20000):
+        c0, c1, bit = rnd.choice([rnd.randrange(65535), 65534, 65533, 0]), rnd.randrange(65535), rnd.getrandbits(1)
+        c = (C.c_uint16 * 2)(c0, c1)
+        libs.oracle.lib.w3o_counter_update(c, bit)
+        got = libs.hostsim.lib.hs_counter_update(c0 | (c1 << 16), bit)
+        assert (got & 0xFFFF, got >> 16) == (c[0], c[1])
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 4, 5, 7, 8, 9, 63, 64, 65, 1000, 1 << 16])
+def test_block_equals_oracle_text(libs, n):
+    data = w3_corpus.generate(n, offset=12345)
+    c = libs.hostsim.compress_block(data)
+    assert c == libs.oracle.compress_block(data)
+    assert libs.hostsim.decompress_block(c, n) == data
+
+
+def test_block_equals_oracle_hostile_inputs(libs):
+    rnd = random.Random(9)
+    cases = [
+        bytes(rnd.getrandbits(8) for _ in range(30000)),
+        bytes(30000),
+        b"\xff" * 30000,
+        bytes(range(256)) * 50,
+        b"\x80" * 9000 + b"\x01" * 9000,
+        bytes((i * 37) & 0xFF for i in range(20000)),
+    ]
+    for data in cases:
+        c = libs.hostsim.compress_block(data)
+        assert c == libs.oracle.compress_block(data)
+        assert libs.hostsim.decompress_block(c, len(data)) == data
+        # truncated stream: zero bits past the end (io.rs:23-25)
+        cut = c[: len(c) // 3]
+        assert libs.hostsim.decompress_block(cut, len(data)) == libs.oracle.decompress_block(cut, len(data))
+
+
+def test_counter_halving_reached(libs):
+    """A block long enough that some counter crosses 65535 and is halved
+    (counter.rs:22-25): alignment-0 context of a constant byte."""
+    data = b"e" * 70000
+    c = libs.hostsim.compress_block(data)
+    assert c == libs.oracle.compress_block(data)
+    assert libs.hostsim.decompress_block(c, len(data)) == data
