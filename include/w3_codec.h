@@ -1,0 +1,116 @@
+/*
+ * w3_codec.h — C ABI of the B200 block-parallel codec for weath3rb0i's
+ * predict→update→code path.  libw3codec.so exports exactly these symbols.
+ *
+ * The reference has no FFI layer; its boundary for this path is the pair of
+ * whole-stream functions private to the binary,
+ *     fn compress(input_file: PathBuf, output_file: PathBuf) -> io::Result<()>   src/main.rs:89
+ *     fn decompress(input_file: PathBuf, output_file: PathBuf) -> io::Result<()> src/main.rs:115
+ * with the model fixed by init_model() (src/main.rs:146-152).  w3_compress /
+ * w3_decompress are those two functions over memory buffers; INTEGRATION.md
+ * shows the `extern "C"` block a maintainer adds to src/main.rs to call them.
+ *
+ * Plain pointers and sizes only; the caller owns every buffer.  All functions
+ * return W3_OK or a negative W3_E_* and never abort.  There is no CPU
+ * fallback: without a usable CUDA device w3_ctx_create fails with W3_E_CUDA.
+ */
+#ifndef W3_CODEC_H
+#define W3_CODEC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define W3_OK 0
+#define W3_E_ARG (-1)    /* bad argument (null pointer, block size, device list) */
+#define W3_E_CAP (-2)    /* output buffer too small; *out_len holds the size needed when known */
+#define W3_E_MAGIC (-3)  /* not a w30i / w3Bk stream — the reference asserts here (src/main.rs:123-124) */
+#define W3_E_CUDA (-4)   /* CUDA error or no device; w3_last_cuda_error() has the text */
+#define W3_E_FORMAT (-5) /* container header or index is inconsistent / truncated */
+#define W3_E_TABLE (-6)  /* threshold-table self-check failed at context creation */
+
+/* flags for w3_compress */
+#define W3_F_LEGACY 1u /* one block, reference file format: "w30i" + u64 BE length + stream
+                          (src/main.rs:14-15, 95-96) — byte-identical to the reference's .bin */
+
+#define W3_MAX_DEVICES 8
+#define W3_DEFAULT_BLOCK (1u << 20)
+
+typedef struct w3_ctx w3_ctx;
+
+/* Creates a codec context on `n_devices` CUDA devices (ordinals in `devices`;
+ * NULL = devices 0..n_devices-1).  Builds the entropy-hash threshold table
+ * for StationaryModel::for_book1 (src/models/ac_hash/stationary.rs:40-42) on
+ * each device.  Blocks are sharded over the devices as contiguous ranges, one
+ * host thread per device, no collective. */
+int w3_ctx_create(const int *devices, int n_devices, w3_ctx **out);
+void w3_ctx_destroy(w3_ctx *ctx);
+int w3_ctx_device_count(const w3_ctx *ctx);
+
+/* Upper bound of w3_compress output for n input bytes. */
+size_t w3_compress_bound(size_t n, size_t block_size);
+
+/* compress() — src/main.rs:89-113 — over host buffers.
+ * Splits in[0..n) into ceil(n / block_size) independent blocks (block_size a
+ * multiple of 4, <= 256 MiB), codes every block exactly as the reference
+ * codes a file of those bytes, and writes the container
+ *   "w3Bk" | u8 version=1 | u8[3] 0 | u64 BE n | u32 BE block_size | u32 BE n_blocks
+ *   | n_blocks x u32 BE stream length | streams back to back
+ * or, with W3_F_LEGACY, the reference's own single-stream file. */
+int w3_compress(w3_ctx *ctx, const uint8_t *in, size_t n, size_t block_size, uint32_t flags,
+                uint8_t *out, size_t cap, size_t *out_len);
+
+/* decompress() — src/main.rs:115-144 — accepts both formats. */
+int w3_decompress(w3_ctx *ctx, const uint8_t *in, size_t n_in, uint8_t *out, size_t cap,
+                  size_t *out_len);
+
+/* Reads only the header: uncompressed length (main.rs:119-126 reads the same field). */
+int w3_decompressed_size(const uint8_t *in, size_t n_in, size_t *out_len);
+
+/* ---- device-resident entry points (inputs already in HBM) ----------------
+ * `dev` indexes the context's device list; `stream` is a cudaStream_t (NULL =
+ * default stream); all work is enqueued on it and the call returns without
+ * synchronising, so the caller can bracket it with CUDA events. */
+
+/* Encodes n_blocks = ceil(n / block_size) blocks from d_in into per-block
+ * scratch regions d_scratch + i * stride (stride a multiple of 4);
+ * d_lens[i] = stream length; *d_overflow != 0 afterwards if any stream did not
+ * fit its region.  d_in must be readable up to the next multiple of 4. */
+int w3_encode_device(w3_ctx *ctx, int dev, const void *d_in, size_t n, size_t block_size,
+                     void *d_scratch, size_t stride, uint32_t *d_lens, uint32_t *d_overflow,
+                     void *stream);
+/* d_offsets[0..n_blocks] = exclusive prefix sum of d_lens; streams copied
+ * back to back into d_packed. */
+int w3_pack_device(w3_ctx *ctx, int dev, const void *d_scratch, size_t stride,
+                   const uint32_t *d_lens, size_t n_blocks, uint64_t *d_offsets, void *d_packed,
+                   void *stream);
+/* Decodes streams d_comp + d_offsets[i] .. d_offsets[i+1] into d_out (n bytes
+ * total, block i at i * block_size).  d_comp needs 8 readable bytes of slack. */
+int w3_decode_device(w3_ctx *ctx, int dev, const void *d_comp, const uint64_t *d_offsets,
+                     size_t n_blocks, size_t block_size, size_t n, void *d_out, void *stream);
+
+/* ---- self-tests of single stages, used by tests/ -------------------------- */
+/* ACHistory::hash (src/history/ac_history.rs:28-46) for n (bits,pos) pairs, host arrays */
+int w3_selftest_achash(w3_ctx *ctx, const uint64_t *bits, const uint32_t *pos, size_t n,
+                       uint32_t *out);
+/* Counter::p (src/models/counter.rs:13-18): all 65535^2 count pairs, float estimate
+ * vs the u64 statement, on the device; *mismatches must come back 0 */
+int w3_selftest_counter_p(w3_ctx *ctx, uint64_t *mismatches);
+/* the coder with caller-supplied probabilities — the harness of
+ * src/entropy_coding/arithmetic_coder_tests.rs:8-42; `in` is read MSB-first */
+int w3_selftest_ac_encode(w3_ctx *ctx, const uint8_t *in, size_t n_in, const uint16_t *probs,
+                          size_t n_probs, uint8_t *out, size_t cap, size_t *out_len);
+int w3_selftest_ac_decode(w3_ctx *ctx, const uint8_t *in, size_t n_in, const uint16_t *probs,
+                          size_t n_probs, uint8_t *out, size_t cap);
+
+const char *w3_strerror(int code);
+const char *w3_last_cuda_error(void);
+const char *w3_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

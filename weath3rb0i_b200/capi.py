@@ -1,0 +1,202 @@
+"""ctypes binding of libw3codec.so (include/w3_codec.h).
+
+There is deliberately no fallback: if the library is missing or no CUDA device
+is usable, importing succeeds but every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libw3codec.so")
+
+W3_OK, W3_E_ARG, W3_E_CAP, W3_E_MAGIC, W3_E_CUDA, W3_E_FORMAT, W3_E_TABLE = 0, -1, -2, -3, -4, -5, -6
+W3_F_LEGACY = 1
+DEFAULT_BLOCK = 1 << 20
+
+# every symbol include/w3_codec.h declares
+SYMBOLS = (
+    "w3_ctx_create", "w3_ctx_destroy", "w3_ctx_device_count", "w3_compress_bound",
+    "w3_compress", "w3_decompress", "w3_decompressed_size",
+    "w3_encode_device", "w3_pack_device", "w3_decode_device",
+    "w3_selftest_achash", "w3_selftest_counter_p", "w3_selftest_ac_encode", "w3_selftest_ac_decode",
+    "w3_strerror", "w3_last_cuda_error", "w3_version",
+)
+
+
+class W3Error(RuntimeError):
+    def __init__(self, code: int, detail: str = ""):
+        self.code = code
+        super().__init__(f"w3 error {code}: {detail}")
+
+
+class MagicMismatch(W3Error):
+    """The reference asserts on a bad magic number (src/main.rs:123-124)."""
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is not built (python -m weath3rb0i_b200.build); "
+            "this codec has no CPU fallback"
+        )
+    lib = C.CDLL(LIB_PATH)
+    sz, vp, u8p = C.c_size_t, C.c_void_p, C.c_void_p
+    lib.w3_ctx_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    lib.w3_ctx_destroy.argtypes = [vp]
+    lib.w3_ctx_destroy.restype = None
+    lib.w3_ctx_device_count.argtypes = [vp]
+    lib.w3_compress_bound.argtypes = [sz, sz]
+    lib.w3_compress_bound.restype = sz
+    lib.w3_compress.argtypes = [vp, u8p, sz, sz, C.c_uint32, u8p, sz, C.POINTER(sz)]
+    lib.w3_decompress.argtypes = [vp, u8p, sz, u8p, sz, C.POINTER(sz)]
+    lib.w3_decompressed_size.argtypes = [u8p, sz, C.POINTER(sz)]
+    lib.w3_encode_device.argtypes = [vp, C.c_int, vp, sz, sz, vp, sz, vp, vp, vp]
+    lib.w3_pack_device.argtypes = [vp, C.c_int, vp, sz, vp, sz, vp, vp, vp]
+    lib.w3_decode_device.argtypes = [vp, C.c_int, vp, vp, sz, sz, sz, vp, vp]
+    lib.w3_selftest_achash.argtypes = [vp, vp, vp, sz, vp]
+    lib.w3_selftest_counter_p.argtypes = [vp, C.POINTER(C.c_uint64)]
+    lib.w3_selftest_ac_encode.argtypes = [vp, u8p, sz, vp, sz, u8p, sz, C.POINTER(sz)]
+    lib.w3_selftest_ac_decode.argtypes = [vp, u8p, sz, vp, sz, u8p, sz]
+    for f in ("w3_strerror", "w3_last_cuda_error", "w3_version"):
+        getattr(lib, f).restype = C.c_char_p
+    lib.w3_strerror.argtypes = [C.c_int]
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc == W3_OK:
+        return
+    lib = load()
+    detail = lib.w3_strerror(rc).decode()
+    if rc == W3_E_CUDA:
+        detail += " — " + lib.w3_last_cuda_error().decode()
+    raise (MagicMismatch if rc == W3_E_MAGIC else W3Error)(rc, detail)
+
+
+def _addr(buf) -> int:
+    """address of a bytes-like / ctypes / numpy / torch host buffer"""
+    if isinstance(buf, int):
+        return buf
+    if hasattr(buf, "data_ptr"):
+        return buf.data_ptr()
+    if hasattr(buf, "ctypes"):
+        return buf.ctypes.data
+    if isinstance(buf, bytes):
+        return C.cast(C.c_char_p(buf), C.c_void_p).value or 0
+    return C.addressof(C.c_char.from_buffer(buf)) if len(buf) else 0
+
+
+class Context:
+    """w3_ctx: one codec context over `devices` (ordinals) of this process."""
+
+    def __init__(self, devices=(0,)):
+        self.lib = load()
+        devices = list(devices)
+        arr = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        check(self.lib.w3_ctx_create(arr, len(devices), C.byref(h)))
+        self.handle = h
+        self.devices = devices
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.w3_ctx_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+    # ---- host-buffer API -------------------------------------------------
+    def compress_bound(self, n: int, block_size: int = DEFAULT_BLOCK) -> int:
+        return self.lib.w3_compress_bound(n, block_size)
+
+    def compress_into(self, src, n: int, dst, cap: int, block_size: int = DEFAULT_BLOCK, legacy=False) -> int:
+        ol = C.c_size_t()
+        check(self.lib.w3_compress(self.handle, _addr(src), n, block_size,
+                                   W3_F_LEGACY if legacy else 0, _addr(dst), cap, C.byref(ol)))
+        return ol.value
+
+    def compress(self, data: bytes, block_size: int = DEFAULT_BLOCK, legacy=False) -> bytes:
+        n = len(data)
+        cap = max(n + n // 4 + 4096, 4096)
+        while True:
+            out = C.create_string_buffer(cap)
+            ol = C.c_size_t()
+            rc = self.lib.w3_compress(self.handle, _addr(data), n, block_size,
+                                      W3_F_LEGACY if legacy else 0, C.addressof(out), cap, C.byref(ol))
+            if rc == W3_E_CAP and ol.value > cap:
+                cap = ol.value
+                continue
+            check(rc)
+            return out.raw[: ol.value]
+
+    def decompressed_size(self, blob: bytes) -> int:
+        ol = C.c_size_t()
+        check(self.lib.w3_decompressed_size(_addr(blob), len(blob), C.byref(ol)))
+        return ol.value
+
+    def decompress_into(self, src, n_in: int, dst, cap: int) -> int:
+        ol = C.c_size_t()
+        check(self.lib.w3_decompress(self.handle, _addr(src), n_in, _addr(dst), cap, C.byref(ol)))
+        return ol.value
+
+    def decompress(self, blob: bytes) -> bytes:
+        n = self.decompressed_size(blob)
+        out = C.create_string_buffer(max(n, 1))
+        ol = C.c_size_t()
+        check(self.lib.w3_decompress(self.handle, _addr(blob), len(blob), C.addressof(out), n, C.byref(ol)))
+        return out.raw[: ol.value]
+
+    # ---- device-resident API (pointers are ints; stream is a cudaStream_t int)
+    def encode_device(self, d_in, n, block_size, d_scratch, stride, d_lens, d_overflow, stream=0, dev=0):
+        check(self.lib.w3_encode_device(self.handle, dev, d_in, n, block_size, d_scratch, stride,
+                                        d_lens, d_overflow, stream))
+
+    def pack_device(self, d_scratch, stride, d_lens, n_blocks, d_offsets, d_packed, stream=0, dev=0):
+        check(self.lib.w3_pack_device(self.handle, dev, d_scratch, stride, d_lens, n_blocks,
+                                      d_offsets, d_packed, stream))
+
+    def decode_device(self, d_comp, d_offsets, n_blocks, block_size, n, d_out, stream=0, dev=0):
+        check(self.lib.w3_decode_device(self.handle, dev, d_comp, d_offsets, n_blocks, block_size,
+                                        n, d_out, stream))
+
+    # ---- stage self-tests ------------------------------------------------
+    def achash(self, bits, pos):
+        n = len(bits)
+        b = (C.c_uint64 * max(n, 1))(*bits)
+        p = (C.c_uint32 * max(n, 1))(*pos)
+        o = (C.c_uint32 * max(n, 1))()
+        check(self.lib.w3_selftest_achash(self.handle, C.addressof(b), C.addressof(p), n, C.addressof(o)))
+        return list(o[:n])
+
+    def counter_p_mismatches(self) -> int:
+        m = C.c_uint64(1)
+        check(self.lib.w3_selftest_counter_p(self.handle, C.byref(m)))
+        return m.value
+
+    def ac_encode_probs(self, data: bytes, probs) -> bytes:
+        n = len(probs)
+        arr = (C.c_uint16 * max(n, 1))(*probs)
+        cap = 4 * n + 16
+        out = C.create_string_buffer(cap)
+        ol = C.c_size_t()
+        check(self.lib.w3_selftest_ac_encode(self.handle, _addr(data), len(data), C.addressof(arr), n,
+                                             C.addressof(out), cap, C.byref(ol)))
+        return out.raw[: ol.value]
+
+    def ac_decode_probs(self, stream: bytes, probs) -> bytes:
+        n = len(probs)
+        arr = (C.c_uint16 * max(n, 1))(*probs)
+        cap = (n + 7) // 8
+        out = C.create_string_buffer(max(cap, 1))
+        check(self.lib.w3_selftest_ac_decode(self.handle, _addr(stream), len(stream), C.addressof(arr), n,
+                                             C.addressof(out), cap))
+        return out.raw[:cap]

@@ -1,0 +1,498 @@
+/*
+ * w3_capi.cu — the C ABI of include/w3_codec.h: block framing, sharding of
+ * blocks over devices (one host thread per device, contiguous ranges, no
+ * collective), staging buffers, and the launches in w3_kernels.cu.
+ *
+ * Mirrors compress()/decompress() of the reference (src/main.rs:89-144): same
+ * header for the single-block "legacy" form, same model (init_model,
+ * src/main.rs:146-152), same behaviour on a bad magic number (an error here,
+ * an assert there).  There is no CPU path: every block is coded by a kernel.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "../../include/w3_codec.h"
+#include "w3_core.cuh"
+#include "w3_kernels.h"
+
+static thread_local char g_cuda_err[256] = "";
+static char g_cuda_err_any[256] = "";
+
+static int cuda_fail(cudaError_t e, const char *what) {
+  snprintf(g_cuda_err, sizeof g_cuda_err, "%s: %s", what, cudaGetErrorString(e));
+  snprintf(g_cuda_err_any, sizeof g_cuda_err_any, "%s", g_cuda_err);
+  return W3_E_CUDA;
+}
+#define CK(call)                                              \
+  do {                                                        \
+    cudaError_t e_ = (call);                                  \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call);       \
+  } while (0)
+
+static const uint8_t MAGIC_LEGACY[4] = {'w', '3', '0', 'i'}; /* src/main.rs:14 */
+static const uint8_t MAGIC_BLOCKS[4] = {'w', '3', 'B', 'k'};
+static const size_t HDR_LEGACY = 12, HDR_BLOCKS = 24;
+static const size_t MAX_BLOCK = (size_t)256 << 20;
+
+struct w3_buf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t n) {
+    if (n <= cap) return W3_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + (n >> 3) + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { e = cudaMalloc(&p, n); want = n; }
+    if (e != cudaSuccess) { p = nullptr; return cuda_fail(e, "cudaMalloc"); }
+    cap = want;
+    return W3_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct w3_dev {
+  int ordinal = 0, sm_count = 148;
+  cudaStream_t stream = nullptr;
+  w3_hashtab *d_tab = nullptr;
+  w3_buf in, scratch, lens, offsets, packed, out;
+  uint32_t *d_flag = nullptr;
+};
+
+struct w3_ctx {
+  int n = 0;
+  w3_dev d[W3_MAX_DEVICES];
+  std::mutex mu; /* one host call at a time per context */
+};
+
+static void put_be32(uint8_t *p, uint32_t v) { for (int i = 0; i < 4; i++) p[i] = (uint8_t)(v >> (24 - 8 * i)); }
+static void put_be64(uint8_t *p, uint64_t v) { for (int i = 0; i < 8; i++) p[i] = (uint8_t)(v >> (56 - 8 * i)); }
+static uint32_t get_be32(const uint8_t *p) { uint32_t v = 0; for (int i = 0; i < 4; i++) v = (v << 8) | p[i]; return v; }
+static uint64_t get_be64(const uint8_t *p) { uint64_t v = 0; for (int i = 0; i < 8; i++) v = (v << 8) | p[i]; return v; }
+static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int dev_init(w3_dev &d, int ordinal) {
+  d.ordinal = ordinal;
+  CK(cudaSetDevice(ordinal));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, ordinal));
+  if (prop.major < 10) {
+    snprintf(g_cuda_err, sizeof g_cuda_err, "device %d is sm_%d%d; this library is built for sm_100a only",
+             ordinal, prop.major, prop.minor);
+    return W3_E_CUDA;
+  }
+  d.sm_count = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+  CK(w3_kernels_init());
+  CK(cudaMalloc(&d.d_tab, sizeof(w3_hashtab)));
+  CK(cudaMalloc(&d.d_flag, sizeof(uint32_t)));
+  std::vector<uint8_t> host(sizeof(w3_hashtab), 0);
+  w3_hashtab *h = reinterpret_cast<w3_hashtab *>(host.data());
+  const uint16_t book1[8] = W3_BOOK1_TABLE; /* init_model — src/main.rs:151 */
+  for (int i = 0; i < 8; i++) h->table[i] = book1[i];
+  h->max_bits = W3_HASH_BITS;
+  CK(cudaMemcpyAsync(d.d_tab, h, sizeof(w3_hashtab), cudaMemcpyHostToDevice, d.stream));
+  CK(w3_launch_build_table(d.d_tab, d.stream));
+  uint16_t bad = 1;
+  CK(cudaMemcpyAsync(&bad, &d.d_tab->bad, sizeof bad, cudaMemcpyDeviceToHost, d.stream));
+  CK(cudaStreamSynchronize(d.stream));
+  return bad ? W3_E_TABLE : W3_OK;
+}
+
+static void dev_release(w3_dev &d) {
+  cudaSetDevice(d.ordinal);
+  d.in.release(); d.scratch.release(); d.lens.release(); d.offsets.release();
+  d.packed.release(); d.out.release();
+  if (d.d_tab) cudaFree(d.d_tab);
+  if (d.d_flag) cudaFree(d.d_flag);
+  if (d.stream) cudaStreamDestroy(d.stream);
+  d.d_tab = nullptr; d.d_flag = nullptr; d.stream = nullptr;
+}
+
+/* run f(g) for every device of the context, on its own host thread when n > 1 */
+template <class F>
+static int for_each_device(w3_ctx *ctx, F &&f) {
+  int rcs[W3_MAX_DEVICES] = {0};
+  if (ctx->n == 1) return f(0);
+  std::vector<std::thread> th;
+  for (int g = 0; g < ctx->n; g++) th.emplace_back([&, g] { rcs[g] = f(g); });
+  for (auto &t : th) t.join();
+  for (int g = 0; g < ctx->n; g++) if (rcs[g] != W3_OK) return rcs[g];
+  return W3_OK;
+}
+
+/* contiguous block range of device g */
+static void block_range(size_t n_blocks, int n_dev, int g, size_t &b0, size_t &b1) {
+  size_t per = (n_blocks + (size_t)n_dev - 1) / (size_t)n_dev;
+  b0 = std::min(n_blocks, per * (size_t)g);
+  b1 = std::min(n_blocks, b0 + per);
+}
+
+extern "C" {
+
+const char *w3_version(void) { return "w3-b200 0.1 (sm_100a)"; }
+const char *w3_last_cuda_error(void) { return g_cuda_err[0] ? g_cuda_err : g_cuda_err_any; }
+const char *w3_strerror(int code) {
+  switch (code) {
+    case W3_OK: return "ok";
+    case W3_E_ARG: return "bad argument";
+    case W3_E_CAP: return "output buffer too small";
+    case W3_E_MAGIC: return "magic numbers don't match up - not a weath3rb0i stream";
+    case W3_E_CUDA: return "CUDA error (see w3_last_cuda_error)";
+    case W3_E_FORMAT: return "inconsistent or truncated block container";
+    case W3_E_TABLE: return "entropy-hash threshold table failed its self-check";
+    default: return "unknown error";
+  }
+}
+
+int w3_ctx_create(const int *devices, int n_devices, w3_ctx **out) {
+  if (!out || n_devices < 1 || n_devices > W3_MAX_DEVICES) return W3_E_ARG;
+  *out = nullptr;
+  int have = 0;
+  cudaError_t e = cudaGetDeviceCount(&have);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+  if (have < 1) { snprintf(g_cuda_err, sizeof g_cuda_err, "no CUDA device"); return W3_E_CUDA; }
+  w3_ctx *ctx = new w3_ctx();
+  for (int i = 0; i < n_devices; i++) {
+    int ord = devices ? devices[i] : i;
+    if (ord < 0 || ord >= have) { w3_ctx_destroy(ctx); return W3_E_ARG; }
+    ctx->n = i + 1;
+    int rc = dev_init(ctx->d[i], ord);
+    if (rc != W3_OK) { w3_ctx_destroy(ctx); return rc; }
+  }
+  *out = ctx;
+  return W3_OK;
+}
+
+void w3_ctx_destroy(w3_ctx *ctx) {
+  if (!ctx) return;
+  for (int i = 0; i < ctx->n; i++) dev_release(ctx->d[i]);
+  delete ctx;
+}
+int w3_ctx_device_count(const w3_ctx *ctx) { return ctx ? ctx->n : 0; }
+
+size_t w3_compress_bound(size_t n, size_t block_size) {
+  if (!block_size) block_size = W3_DEFAULT_BLOCK;
+  size_t nb = (n + block_size - 1) / block_size;
+  /* <= 16.001 coded bits per input bit (p >= 2^-16), + flush, per block */
+  return HDR_BLOCKS + 4 * nb + 17 * n + 8 * (nb + 1);
+}
+
+/* ---- device-resident entry points ---------------------------------------- */
+
+int w3_encode_device(w3_ctx *ctx, int dev, const void *d_in, size_t n, size_t block_size,
+                     void *d_scratch, size_t stride, uint32_t *d_lens, uint32_t *d_overflow,
+                     void *stream) {
+  if (!ctx || dev < 0 || dev >= ctx->n || !block_size || (block_size & 3) || block_size > MAX_BLOCK ||
+      (stride & 3) || !d_lens || !d_overflow)
+    return W3_E_ARG;
+  size_t nb = (n + block_size - 1) / block_size;
+  if (!nb) return W3_OK;
+  if (!d_in || !d_scratch || nb > 0xFFFFFFFFull) return W3_E_ARG;
+  w3_dev &d = ctx->d[dev];
+  CK(cudaSetDevice(d.ordinal));
+  CK(w3_launch_encode((const uint8_t *)d_in, n, (uint32_t)block_size, (uint32_t)nb,
+                      (uint8_t *)d_scratch, stride, d_lens, d_overflow, d.d_tab, d.sm_count,
+                      (cudaStream_t)stream));
+  return W3_OK;
+}
+
+int w3_pack_device(w3_ctx *ctx, int dev, const void *d_scratch, size_t stride,
+                   const uint32_t *d_lens, size_t n_blocks, uint64_t *d_offsets, void *d_packed,
+                   void *stream) {
+  if (!ctx || dev < 0 || dev >= ctx->n || !d_offsets || n_blocks > 0xFFFFFFFFull) return W3_E_ARG;
+  if (n_blocks && (!d_scratch || !d_lens || !d_packed)) return W3_E_ARG;
+  w3_dev &d = ctx->d[dev];
+  CK(cudaSetDevice(d.ordinal));
+  CK(w3_launch_pack((const uint8_t *)d_scratch, stride, d_lens, (uint32_t)n_blocks, d_offsets,
+                    (uint8_t *)d_packed, (cudaStream_t)stream));
+  return W3_OK;
+}
+
+int w3_decode_device(w3_ctx *ctx, int dev, const void *d_comp, const uint64_t *d_offsets,
+                     size_t n_blocks, size_t block_size, size_t n, void *d_out, void *stream) {
+  if (!ctx || dev < 0 || dev >= ctx->n || !block_size || (block_size & 3) || block_size > MAX_BLOCK)
+    return W3_E_ARG;
+  if (n_blocks != (n + block_size - 1) / block_size || n_blocks > 0xFFFFFFFFull) return W3_E_ARG;
+  if (!n_blocks) return W3_OK;
+  if (!d_comp || !d_offsets || !d_out) return W3_E_ARG;
+  w3_dev &d = ctx->d[dev];
+  CK(cudaSetDevice(d.ordinal));
+  CK(w3_launch_decode((const uint8_t *)d_comp, d_offsets, (uint32_t)n_blocks, (uint32_t)block_size,
+                      n, (uint8_t *)d_out, d.d_tab, d.sm_count, (cudaStream_t)stream));
+  return W3_OK;
+}
+
+/* ---- host-buffer entry points -------------------------------------------- */
+
+struct enc_part {
+  size_t b0 = 0, b1 = 0;
+  uint64_t total = 0;
+  std::vector<uint32_t> lens;
+};
+
+/* encode blocks [b0,b1) of `in` on device g; leaves the packed streams in
+ * d.packed and their lengths in part.lens */
+static int encode_part(w3_ctx *ctx, int g, const uint8_t *in, size_t n, size_t bs, enc_part &part) {
+  w3_dev &d = ctx->d[g];
+  const size_t nb = part.b1 - part.b0;
+  part.lens.assign(nb, 0);
+  part.total = 0;
+  if (!nb) return W3_OK;
+  CK(cudaSetDevice(d.ordinal));
+  const size_t off = part.b0 * bs;
+  const size_t bytes = std::min(n, part.b1 * bs) - off;
+  int rc;
+  if ((rc = d.in.ensure(round_up(bytes, 4) + 16)) != W3_OK) return rc;
+  if ((rc = d.lens.ensure(nb * 4)) != W3_OK) return rc;
+  if ((rc = d.offsets.ensure((nb + 1) * 8)) != W3_OK) return rc;
+  CK(cudaMemcpyAsync(d.in.p, in + off, bytes, cudaMemcpyHostToDevice, d.stream));
+  /* text codes to ~0.45 n; leave generous room and retry at the hard bound
+   * (17 n: p >= 2^-16 caps the cost of one bit at 16 + eps bits) on overflow */
+  size_t stride = round_up(bs + (bs >> 3) + 64, 16);
+  for (int attempt = 0;; attempt++) {
+    if ((rc = d.scratch.ensure(stride * nb)) != W3_OK) return rc;
+    CK(cudaMemsetAsync(d.d_flag, 0, 4, d.stream));
+    CK(w3_launch_encode((const uint8_t *)d.in.p, bytes, (uint32_t)bs, (uint32_t)nb,
+                        (uint8_t *)d.scratch.p, stride, (uint32_t *)d.lens.p, d.d_flag, d.d_tab,
+                        d.sm_count, d.stream));
+    uint32_t flag = 0;
+    CK(cudaMemcpyAsync(&flag, d.d_flag, 4, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaMemcpyAsync(part.lens.data(), d.lens.p, nb * 4, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    if (!flag) break;
+    if (attempt) { snprintf(g_cuda_err, sizeof g_cuda_err, "stream exceeded the 17n bound"); return W3_E_CUDA; }
+    stride = round_up(17 * bs + 64, 16);
+  }
+  for (uint32_t l : part.lens) part.total += l;
+  if ((rc = d.packed.ensure(part.total + 16)) != W3_OK) return rc;
+  CK(w3_launch_pack((const uint8_t *)d.scratch.p, stride, (const uint32_t *)d.lens.p, (uint32_t)nb,
+                    (uint64_t *)d.offsets.p, (uint8_t *)d.packed.p, d.stream));
+  return W3_OK;
+}
+
+int w3_compress(w3_ctx *ctx, const uint8_t *in, size_t n, size_t block_size, uint32_t flags,
+                uint8_t *out, size_t cap, size_t *out_len) {
+  if (!ctx || !out_len || (!in && n) || (!out && cap)) return W3_E_ARG;
+  const bool legacy = flags & W3_F_LEGACY;
+  if (legacy) block_size = std::max<size_t>(round_up(n, 4), 4);
+  if (!block_size) block_size = W3_DEFAULT_BLOCK;
+  if ((block_size & 3) || block_size > MAX_BLOCK) return W3_E_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  /* the reference codes an empty file as one empty stream (0xff); keep that
+   * in legacy form, and an empty container has zero blocks */
+  const size_t nb = legacy ? 1 : (n + block_size - 1) / block_size;
+  if (nb > 0xFFFFFFFFull) return W3_E_ARG;
+  const size_t hdr = legacy ? HDR_LEGACY : HDR_BLOCKS + 4 * nb;
+
+  enc_part parts[W3_MAX_DEVICES];
+  for (int g = 0; g < ctx->n; g++) block_range(nb, ctx->n, g, parts[g].b0, parts[g].b1);
+  int rc;
+  if (legacy && n == 0) {
+    /* zero-length block: the kernel still runs (flush only) */
+    parts[0].b0 = 0; parts[0].b1 = 1;
+    for (int g = 1; g < ctx->n; g++) parts[g].b0 = parts[g].b1 = 1;
+  }
+  rc = for_each_device(ctx, [&](int g) { return encode_part(ctx, g, in, n, block_size, parts[g]); });
+  if (rc != W3_OK) return rc;
+
+  uint64_t total = 0;
+  for (int g = 0; g < ctx->n; g++) total += parts[g].total;
+  *out_len = hdr + total;
+  if (*out_len > cap) return W3_E_CAP;
+
+  if (legacy) {
+    memcpy(out, MAGIC_LEGACY, 4);   /* main.rs:95 */
+    put_be64(out + 4, (uint64_t)n); /* main.rs:96 */
+  } else {
+    memcpy(out, MAGIC_BLOCKS, 4);
+    out[4] = 1; out[5] = out[6] = out[7] = 0;
+    put_be64(out + 8, (uint64_t)n);
+    put_be32(out + 16, (uint32_t)block_size);
+    put_be32(out + 20, (uint32_t)nb);
+    uint8_t *idx = out + HDR_BLOCKS;
+    for (int g = 0; g < ctx->n; g++)
+      for (uint32_t l : parts[g].lens) { put_be32(idx, l); idx += 4; }
+  }
+  uint64_t base[W3_MAX_DEVICES], run = hdr;
+  for (int g = 0; g < ctx->n; g++) { base[g] = run; run += parts[g].total; }
+  return for_each_device(ctx, [&](int g) {
+    w3_dev &d = ctx->d[g];
+    if (!parts[g].total) return (int)W3_OK;
+    CK(cudaSetDevice(d.ordinal));
+    CK(cudaMemcpyAsync(out + base[g], d.packed.p, parts[g].total, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    return (int)W3_OK;
+  });
+}
+
+int w3_decompressed_size(const uint8_t *in, size_t n_in, size_t *out_len) {
+  if (!in || !out_len) return W3_E_ARG;
+  if (n_in < 4) return W3_E_MAGIC; /* read_exact fails in the reference (main.rs:121) */
+  if (!memcmp(in, MAGIC_LEGACY, 4)) {
+    if (n_in < HDR_LEGACY) return W3_E_FORMAT;
+    *out_len = (size_t)get_be64(in + 4);
+    return W3_OK;
+  }
+  if (!memcmp(in, MAGIC_BLOCKS, 4)) {
+    if (n_in < HDR_BLOCKS || in[4] != 1) return W3_E_FORMAT;
+    *out_len = (size_t)get_be64(in + 8);
+    return W3_OK;
+  }
+  return W3_E_MAGIC;
+}
+
+int w3_decompress(w3_ctx *ctx, const uint8_t *in, size_t n_in, uint8_t *out, size_t cap,
+                  size_t *out_len) {
+  if (!ctx || !in || !out_len || (!out && cap)) return W3_E_ARG;
+  size_t n = 0;
+  int rc = w3_decompressed_size(in, n_in, &n);
+  if (rc != W3_OK) return rc;
+  *out_len = n;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+
+  size_t bs, nb, hdr;
+  std::vector<uint64_t> offs; /* nb + 1, relative to the first stream byte */
+  if (!memcmp(in, MAGIC_LEGACY, 4)) {
+    /* one stream running to the end of the file; a short file decodes with
+     * zero bits past its end, as ACReader does (io.rs:23-25) */
+    bs = std::max<size_t>(round_up(n, 4), 4);
+    if (bs > MAX_BLOCK) return W3_E_ARG;
+    nb = n ? 1 : 0;
+    hdr = HDR_LEGACY;
+    offs = {0, n_in - hdr};
+  } else {
+    bs = get_be32(in + 16);
+    nb = get_be32(in + 20);
+    if (!bs || (bs & 3) || bs > MAX_BLOCK || nb != (n + bs - 1) / bs) return W3_E_FORMAT;
+    hdr = HDR_BLOCKS + 4 * nb;
+    if (n_in < hdr) return W3_E_FORMAT;
+    offs.resize(nb + 1);
+    uint64_t run = 0;
+    for (size_t i = 0; i < nb; i++) { offs[i] = run; run += get_be32(in + HDR_BLOCKS + 4 * i); }
+    offs[nb] = run;
+    if (hdr + run != n_in) return W3_E_FORMAT;
+  }
+  if (n > cap) return W3_E_CAP;
+  if (!nb) return W3_OK;
+
+  return for_each_device(ctx, [&](int g) {
+    size_t b0, b1;
+    block_range(nb, ctx->n, g, b0, b1);
+    if (b0 == b1) return (int)W3_OK;
+    w3_dev &d = ctx->d[g];
+    CK(cudaSetDevice(d.ordinal));
+    const size_t nbg = b1 - b0;
+    const uint64_t c0 = offs[b0], clen = offs[b1] - c0;
+    const size_t o0 = b0 * bs, obytes = std::min(n, b1 * bs) - o0;
+    int r;
+    if ((r = d.packed.ensure(clen + 16)) != W3_OK) return r;
+    if ((r = d.offsets.ensure((nbg + 1) * 8)) != W3_OK) return r;
+    if ((r = d.out.ensure(round_up(obytes, 4) + 16)) != W3_OK) return r;
+    std::vector<uint64_t> rel(nbg + 1);
+    for (size_t i = 0; i <= nbg; i++) rel[i] = offs[b0 + i] - c0;
+    CK(cudaMemsetAsync((uint8_t *)d.packed.p + clen, 0, 16, d.stream));
+    if (clen) CK(cudaMemcpyAsync(d.packed.p, in + hdr + c0, clen, cudaMemcpyHostToDevice, d.stream));
+    CK(cudaMemcpyAsync(d.offsets.p, rel.data(), (nbg + 1) * 8, cudaMemcpyHostToDevice, d.stream));
+    CK(w3_launch_decode((const uint8_t *)d.packed.p, (const uint64_t *)d.offsets.p, (uint32_t)nbg,
+                        (uint32_t)bs, obytes, (uint8_t *)d.out.p, d.d_tab, d.sm_count, d.stream));
+    CK(cudaMemcpyAsync(out + o0, d.out.p, obytes, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    return (int)W3_OK;
+  });
+}
+
+/* ---- self-tests ------------------------------------------------------------ */
+
+int w3_selftest_achash(w3_ctx *ctx, const uint64_t *bits, const uint32_t *pos, size_t n,
+                       uint32_t *out) {
+  if (!ctx || !bits || !pos || !out || n > 0xFFFFFFFFull) return W3_E_ARG;
+  if (!n) return W3_OK;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  w3_dev &d = ctx->d[0];
+  CK(cudaSetDevice(d.ordinal));
+  int rc;
+  if ((rc = d.in.ensure(n * 8)) != W3_OK) return rc;
+  if ((rc = d.lens.ensure(n * 4)) != W3_OK) return rc;
+  if ((rc = d.out.ensure(n * 4)) != W3_OK) return rc;
+  CK(cudaMemcpyAsync(d.in.p, bits, n * 8, cudaMemcpyHostToDevice, d.stream));
+  CK(cudaMemcpyAsync(d.lens.p, pos, n * 4, cudaMemcpyHostToDevice, d.stream));
+  CK(w3_launch_hash_array((const uint64_t *)d.in.p, (const uint32_t *)d.lens.p, (uint32_t)n,
+                          (uint32_t *)d.out.p, d.d_tab, d.stream));
+  CK(cudaMemcpyAsync(out, d.out.p, n * 4, cudaMemcpyDeviceToHost, d.stream));
+  CK(cudaStreamSynchronize(d.stream));
+  return W3_OK;
+}
+
+int w3_selftest_counter_p(w3_ctx *ctx, uint64_t *mismatches) {
+  if (!ctx || !mismatches) return W3_E_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  w3_dev &d = ctx->d[0];
+  CK(cudaSetDevice(d.ordinal));
+  int rc;
+  if ((rc = d.offsets.ensure(8)) != W3_OK) return rc;
+  CK(cudaMemsetAsync(d.offsets.p, 0, 8, d.stream));
+  CK(w3_launch_counter_p_check((unsigned long long *)d.offsets.p, d.stream));
+  CK(cudaMemcpyAsync(mismatches, d.offsets.p, 8, cudaMemcpyDeviceToHost, d.stream));
+  CK(cudaStreamSynchronize(d.stream));
+  return W3_OK;
+}
+
+int w3_selftest_ac_encode(w3_ctx *ctx, const uint8_t *in, size_t n_in, const uint16_t *probs,
+                          size_t n_probs, uint8_t *out, size_t cap, size_t *out_len) {
+  if (!ctx || !in || !probs || !out || !out_len || n_in * 8 < n_probs || n_probs > 0x7FFFFFFF)
+    return W3_E_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  w3_dev &d = ctx->d[0];
+  CK(cudaSetDevice(d.ordinal));
+  int rc;
+  if ((rc = d.in.ensure(n_in + 16)) != W3_OK) return rc;
+  if ((rc = d.scratch.ensure(n_probs * 2 + 16)) != W3_OK) return rc;
+  if ((rc = d.out.ensure(cap + 16)) != W3_OK) return rc;
+  if ((rc = d.lens.ensure(4)) != W3_OK) return rc;
+  CK(cudaMemcpyAsync(d.in.p, in, n_in, cudaMemcpyHostToDevice, d.stream));
+  CK(cudaMemcpyAsync(d.scratch.p, probs, n_probs * 2, cudaMemcpyHostToDevice, d.stream));
+  CK(w3_launch_ac_encode_probs((const uint8_t *)d.in.p, (const uint16_t *)d.scratch.p,
+                               (uint32_t)n_probs, (uint8_t *)d.out.p, (uint32_t)cap,
+                               (uint32_t *)d.lens.p, d.stream));
+  uint32_t len = 0;
+  CK(cudaMemcpyAsync(&len, d.lens.p, 4, cudaMemcpyDeviceToHost, d.stream));
+  CK(cudaStreamSynchronize(d.stream));
+  *out_len = len;
+  if (len > cap) return W3_E_CAP;
+  CK(cudaMemcpy(out, d.out.p, len, cudaMemcpyDeviceToHost));
+  return W3_OK;
+}
+
+int w3_selftest_ac_decode(w3_ctx *ctx, const uint8_t *in, size_t n_in, const uint16_t *probs,
+                          size_t n_probs, uint8_t *out, size_t cap) {
+  if (!ctx || !in || !probs || !out || cap * 8 < n_probs || n_probs > 0x7FFFFFFF) return W3_E_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  w3_dev &d = ctx->d[0];
+  CK(cudaSetDevice(d.ordinal));
+  int rc;
+  if ((rc = d.in.ensure(n_in + 16)) != W3_OK) return rc;
+  if ((rc = d.scratch.ensure(n_probs * 2 + 16)) != W3_OK) return rc;
+  if ((rc = d.out.ensure(cap + 16)) != W3_OK) return rc;
+  CK(cudaMemsetAsync(d.in.p, 0, n_in + 16, d.stream));
+  CK(cudaMemcpyAsync(d.in.p, in, n_in, cudaMemcpyHostToDevice, d.stream));
+  CK(cudaMemcpyAsync(d.scratch.p, probs, n_probs * 2, cudaMemcpyHostToDevice, d.stream));
+  CK(w3_launch_ac_decode_probs((const uint8_t *)d.in.p, (uint32_t)n_in, (const uint16_t *)d.scratch.p,
+                               (uint32_t)n_probs, (uint8_t *)d.out.p, d.stream));
+  CK(cudaMemcpyAsync(out, d.out.p, (n_probs + 7) / 8, cudaMemcpyDeviceToHost, d.stream));
+  CK(cudaStreamSynchronize(d.stream));
+  return W3_OK;
+}
+
+} /* extern "C" */

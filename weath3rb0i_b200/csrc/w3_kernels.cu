@@ -1,0 +1,522 @@
+/*
+ * w3_kernels.cu — sm_100a kernels for weath3rb0i's predict→update→code path
+ * (reference: src/main.rs:89-152 and everything it calls).
+ *
+ * One warp owns one block (an independent stream with fresh counters, history
+ * and coder, exactly what the reference does for one file):
+ *
+ *   encode  lanes = 32 consecutive bit positions.  Each lane rebuilds its own
+ *           64-bit history from the input words, finds its context through
+ *           the shared-memory threshold table (w3_hash_lookup), resolves the
+ *           counter it would have seen with __match_any_sync + popcounts,
+ *           divides (Counter::p) — all 32 in parallel — and then the 32
+ *           (bit, p) pairs go through the arithmetic coder in order.
+ *   decode  strictly serial per stream (bit → history → context → p → bit).
+ *           Lanes speculate: see w3_decode_blocks.
+ *
+ * Per-block adaptive state is 8 KiB of counters and lives in shared memory
+ * together with one copy of the 50 KiB threshold table per CTA; HBM sees only
+ * the input and output streams.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "w3_core.cuh"
+#include "w3_kernels.h"
+
+#define FULL 0xFFFFFFFFu
+
+/* ------------------------------------------------------------------------ */
+/* threshold-table construction (context creation)                          */
+
+__global__ void w3_k_build_thr(w3_hashtab *tab) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 8u * 256u) w3_build_thr(tab, i >> 8, i & 255u);
+}
+__global__ void w3_k_build_cell_rval(w3_hashtab *tab) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 8u * W3_NCELL) w3_build_cell(tab, i / W3_NCELL, i % W3_NCELL);
+  if (i < 8u * 256u) w3_build_rval(tab, i >> 8, i & 255u);
+}
+
+/* ------------------------------------------------------------------------ */
+/* shared-memory layout                                                     */
+
+struct w3_smem_tab {
+  uint64_t thr[8 * 256];
+  uint16_t cell[8 * W3_NCELL];
+  uint8_t rval[8 * 256];
+  uint16_t table[8];
+  uint32_t max_bits;
+  uint32_t pad[3];
+};
+static_assert(sizeof(w3_smem_tab) % 16 == 0, "smem table must keep 16-byte alignment");
+
+__device__ __forceinline__ void w3_load_tab(w3_smem_tab *s, const w3_hashtab *g) {
+  const uint32_t tid = threadIdx.x, nt = blockDim.x;
+  const uint4 *gt = reinterpret_cast<const uint4 *>(&g->thr[0][0]);
+  uint4 *st = reinterpret_cast<uint4 *>(s->thr);
+  for (uint32_t i = tid; i < sizeof(s->thr) / 16; i += nt) st[i] = gt[i];
+  const uint4 *gc = reinterpret_cast<const uint4 *>(&g->cell[0][0]);
+  uint4 *sc = reinterpret_cast<uint4 *>(s->cell);
+  for (uint32_t i = tid; i < sizeof(s->cell) / 16; i += nt) sc[i] = gc[i];
+  const uint4 *gr = reinterpret_cast<const uint4 *>(&g->rval[0][0]);
+  uint4 *sr = reinterpret_cast<uint4 *>(s->rval);
+  for (uint32_t i = tid; i < sizeof(s->rval) / 16; i += nt) sr[i] = gr[i];
+  if (tid < 8) s->table[tid] = g->table[tid];
+  if (tid == 0) s->max_bits = g->max_bits;
+}
+
+/* ACHistory::hash through the table, literal loop for threshold keys */
+__device__ __forceinline__ uint32_t w3_hash_dev(const w3_smem_tab *s, uint64_t key, uint32_t pos) {
+  uint32_t h = w3_hash_lookup(key, pos & 7u, s->thr, s->cell, s->rval);
+  if (h == 0xFFFFFFFFu)
+    h = w3_achash_exact(w3_key_of_history(key), pos, s->table, (int)s->max_bits).hash;
+  return h;
+}
+
+__device__ __forceinline__ uint32_t w3_bswap(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+
+/* ------------------------------------------------------------------------ */
+/* encode: one warp per block                                               */
+
+__global__ void __launch_bounds__(W3_MAX_WARPS * 32)
+w3_encode_blocks(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t block_size,
+                 uint32_t n_blocks, uint8_t *__restrict__ scratch, uint64_t stride,
+                 uint32_t *__restrict__ lens, uint32_t *__restrict__ overflow,
+                 const w3_hashtab *__restrict__ tab) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  w3_smem_tab *st = reinterpret_cast<w3_smem_tab *>(smem_raw);
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  uint32_t *stats = reinterpret_cast<uint32_t *>(smem_raw + sizeof(w3_smem_tab)) + warp * W3_NCTX;
+
+  w3_load_tab(st, tab);
+  for (uint32_t i = lane; i < W3_NCTX; i += 32) stats[i] = 0u; /* ordern_entropy.rs:17 */
+  __syncthreads();
+
+  const uint32_t blk = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (blk >= n_blocks) return;
+  const uint64_t off = (uint64_t)blk * block_size;
+  const uint32_t n = (uint32_t)(n_total - off < block_size ? n_total - off : block_size);
+  const uint32_t *src = reinterpret_cast<const uint32_t *>(in + off);
+  uint32_t *dst = reinterpret_cast<uint32_t *>(scratch + (uint64_t)blk * stride);
+  const uint32_t cap_words = (uint32_t)(stride >> 2);
+
+  uint32_t ovf = 0;
+  auto store = [&](uint32_t idx, uint32_t v) {
+    if (lane == 0) {
+      if (idx < cap_words) dst[idx] = w3_bswap(v);
+      else ovf = 1;
+    }
+  };
+
+  uint32_t x1 = 0, x2 = 0xFFFFFFFFu; /* new_coder — arithmetic_coder.rs:37-39 */
+  w3_writer wr;
+  w3_writer_init(wr);
+
+  const uint32_t n_words = (n + 3u) >> 2;
+  auto load_chunk = [&](uint32_t chunk) -> uint32_t {
+    uint32_t widx = chunk * 32u + lane, v = 0;
+    if (widx < n_words) {
+      v = w3_bswap(__ldg(src + widx));
+      uint32_t rem = n - widx * 4u; /* bytes of this word inside the block */
+      if (rem < 4u) v &= 0xFFFFFFFFu << (8u * (4u - rem));
+    }
+    return v;
+  };
+
+  uint32_t w0 = 0, w1 = 0; /* the 64 stream bits before the current word */
+  uint32_t cw_next = load_chunk(0);
+  for (uint32_t chunk = 0; chunk * 32u < n_words; chunk++) {
+    const uint32_t cw = cw_next;
+    cw_next = load_chunk(chunk + 1);
+    const uint32_t in_chunk = n_words - chunk * 32u < 32u ? n_words - chunk * 32u : 32u;
+    for (uint32_t i = 0; i < in_chunk; i++) {
+      const uint32_t w2 = __shfl_sync(FULL, cw, i);
+      const uint32_t g = chunk * 32u + i;   /* word index = group of 32 bits */
+      const uint32_t left = n * 8u - g * 32u; /* coded bits left in the block */
+      const uint32_t nact = left < 32u ? left : 32u;
+      const bool active = lane < nact;
+      const uint32_t t = g * 32u + lane;    /* bits coded before this one */
+
+      /* ACHistory.bits as seen by bit t: the 64 stream bits before it */
+      const uint32_t hist_hi = __funnelshift_l(w1, w0, lane);
+      const uint32_t hist_lo = __funnelshift_l(w2, w1, lane);
+      const uint32_t bit = (w2 >> (31u - lane)) & 1u;
+      const uint64_t key = ((uint64_t)__brev(hist_lo) << 32) | __brev(hist_hi);
+
+      /* ctx = (hash << 3) | alignment — ordern_entropy.rs:43-44; ctx_0 = 0 (:20) */
+      uint32_t ctx = (w3_hash_dev(st, key, t) << W3_ALIGN_BITS) | (t & 7u);
+      if (t == 0) ctx = 0;
+      if (!active) ctx = 0x10000u | lane; /* unique: matches nobody */
+
+      /* counter state each lane would see in sequential order */
+      const uint32_t m = __match_any_sync(FULL, ctx);
+      const uint32_t bm = __ballot_sync(FULL, active && bit);
+      const uint32_t slot = active ? stats[ctx] : 0u;
+      const uint32_t lower = m & ((1u << lane) - 1u);
+      const uint32_t e1 = __popc(lower & bm), e0 = __popc(lower) - e1;
+      const uint32_t t1 = __popc(m & bm), t0 = __popc(m) - t1;
+      const uint32_t c0 = slot & 0xFFFFu, c1 = slot >> 16;
+      const bool risky = active && (c0 + t0 >= 0xFFFFu || c1 + t1 >= 0xFFFFu);
+      uint32_t p;
+      __syncwarp();
+      if (__any_sync(FULL, risky)) {
+        /* a halving (counter.rs:22-25) may fall inside this group: replay it
+         * in order, one lane at a time */
+        p = 0;
+        for (uint32_t j = 0; j < nact; j++) {
+          if (lane == j) {
+            uint32_t sl = stats[ctx];
+            p = w3_counter_p(sl & 0xFFFFu, sl >> 16);
+            stats[ctx] = w3_counter_update(sl, bit);
+          }
+          __syncwarp();
+        }
+      } else {
+        p = w3_counter_p(c0 + e0, c1 + e1);                /* predict — main.rs:105 */
+        if (active && lane == 31u - (uint32_t)__clz((int)m)) /* last of its group */
+          stats[ctx] = (c0 + t0) | ((c1 + t1) << 16);      /* adapt — main.rs:106 */
+      }
+      __syncwarp();
+
+      /* ac.encode(bit, p) in order — main.rs:107 */
+      const uint32_t P = p << 16; /* p in [1,65535], so lerp's prob==0 arm is dead */
+      for (uint32_t j = 0; j < nact; j++) {
+        const uint32_t Pj = __shfl_sync(FULL, P, j);
+        w3_ac_narrow(x1, x2, (bm >> j) & 1u, Pj);
+        const uint32_t pre = x1;
+        int s, k;
+        w3_ac_renorm(x1, x2, s, k);
+        w3_writer_step(wr, pre, s, k, store);
+      }
+      w0 = w1;
+      w1 = w2;
+    }
+  }
+
+  /* ac.flush — main.rs:111 */
+  uint32_t tail, tail_bytes;
+  const uint64_t len = w3_writer_flush(wr, x2, tail, tail_bytes, store);
+  if (lane == 0) {
+    uint8_t *tb = reinterpret_cast<uint8_t *>(dst) + (uint64_t)wr.words * 4u;
+    for (uint32_t b = 0; b < tail_bytes; b++) {
+      if ((uint64_t)wr.words * 4u + b < stride) tb[b] = (uint8_t)(tail >> (24u - 8u * b));
+      else ovf = 1;
+    }
+    lens[blk] = (uint32_t)len;
+    if (ovf) atomicOr(overflow, 1u);
+  }
+}
+
+/* ------------------------------------------------------------------------ */
+/* decode: one warp per block                                               */
+
+/* MSB-first bit source over a byte range at any alignment; zero bits past the
+ * end (ACReader — src/entropy_coding/io.rs:18-48).  Loads run two words ahead
+ * of use so their latency stays off the decode chain. */
+struct w3_reader {
+  const uint32_t *ab; /* aligned base */
+  uint32_t sel;       /* __byte_perm selector for the start misalignment */
+  int64_t slen;       /* stream length in bytes */
+  uint32_t widx;      /* next stream word to assemble */
+  uint32_t cur, nxt;  /* ab[widx], ab[widx+1] */
+  uint64_t win;       /* upcoming bits, left aligned */
+  int have;
+};
+
+__device__ __forceinline__ uint32_t w3_reader_ld(const w3_reader &r, uint32_t i) {
+  /* aligned word i of the range, 0 when it lies wholly past the stream's end
+   * (the caller guarantees 8 bytes of slack after the buffer) */
+  return ((int64_t)i * 4 < r.slen + 4) ? __ldg(r.ab + i) : 0u;
+}
+__device__ __forceinline__ uint32_t w3_reader_word(w3_reader &r) {
+  uint32_t v = __byte_perm(r.cur, r.nxt, r.sel);
+  int64_t rem = r.slen - (int64_t)r.widx * 4;
+  if (rem < 4) v = rem <= 0 ? 0u : (v & (0xFFFFFFFFu << (8 * (4 - (int)rem))));
+  r.widx++;
+  r.cur = r.nxt;
+  r.nxt = w3_reader_ld(r, r.widx + 1);
+  return v;
+}
+__device__ __forceinline__ void w3_reader_init(w3_reader &r, const uint8_t *p, uint64_t slen) {
+  uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u);
+  r.ab = reinterpret_cast<const uint32_t *>(p - sh);
+  r.sel = ((sh + 3u) | ((sh + 2u) << 4) | ((sh + 1u) << 8) | (sh << 12));
+  r.slen = (int64_t)slen;
+  r.widx = 0;
+  r.cur = w3_reader_ld(r, 0);
+  r.nxt = w3_reader_ld(r, 1);
+  uint32_t a = w3_reader_word(r), b = w3_reader_word(r);
+  r.win = ((uint64_t)a << 32) | b;
+  r.have = 64;
+}
+__device__ __forceinline__ uint32_t w3_reader_take(w3_reader &r, int c) { /* c in [1,32] */
+  uint32_t v = (uint32_t)(r.win >> (64 - c));
+  r.win = c == 32 ? r.win << 32 : r.win << c;
+  r.have -= c;
+  if (r.have <= 32) {
+    r.win |= (uint64_t)w3_reader_word(r) << (32 - r.have);
+    r.have += 32;
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(W3_MAX_WARPS * 32)
+w3_decode_blocks(const uint8_t *__restrict__ comp, const uint64_t *__restrict__ offsets,
+                 uint32_t n_blocks, uint32_t block_size, uint64_t n_total,
+                 uint8_t *__restrict__ out, const w3_hashtab *__restrict__ tab) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  w3_smem_tab *st = reinterpret_cast<w3_smem_tab *>(smem_raw);
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  uint32_t *stats = reinterpret_cast<uint32_t *>(smem_raw + sizeof(w3_smem_tab)) + warp * W3_NCTX;
+
+  w3_load_tab(st, tab);
+  for (uint32_t i = lane; i < W3_NCTX; i += 32) stats[i] = 0u;
+  __syncthreads();
+
+  const uint32_t blk = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (blk >= n_blocks) return;
+  const uint64_t off = (uint64_t)blk * block_size;
+  const uint32_t n = (uint32_t)(n_total - off < block_size ? n_total - off : block_size);
+  uint8_t *dst = out + off;
+
+  w3_reader rd;
+  w3_reader_init(rd, comp + offsets[blk], offsets[blk + 1] - offsets[blk]);
+  uint32_t x1 = 0, x2 = 0xFFFFFFFFu;
+  uint32_t x = w3_reader_take(rd, 32); /* new_decoder — arithmetic_coder.rs:75-78 */
+  uint64_t key = 0;                    /* ACHistory.bits, newest bit at bit 63 */
+  uint32_t ctx = 0, t = 0, word = 0;
+
+  for (uint32_t i = 0; i < n; i++) {
+    uint32_t byte = 0;
+#pragma unroll
+    for (int kb = 0; kb < 8; kb++) {
+      const uint32_t slot = stats[ctx];
+      const uint32_t P = w3_counter_p(slot & 0xFFFFu, slot >> 16) << 16; /* main.rs:134 */
+      const uint32_t xmid = x1 + __umulhi(x2 - x1, P);
+      const uint32_t bit = x <= xmid ? 1u : 0u;                          /* :82 */
+      if (bit) x2 = xmid; else x1 = xmid + 1u;
+      int s, k;
+      const int nsh = w3_ac_renorm(x1, x2, s, k);
+      if (nsh) x = ((x << nsh) | w3_reader_take(rd, nsh)) ^ (k ? 0x80000000u : 0u);
+      __syncwarp();
+      if (lane == 0) stats[ctx] = w3_counter_update(slot, bit);          /* main.rs:136 */
+      __syncwarp();
+      key = (key >> 1) | ((uint64_t)bit << 63);
+      t++;
+      ctx = (w3_hash_dev(st, key, t) << W3_ALIGN_BITS) | (t & 7u);
+      byte = (byte << 1) | bit;
+    }
+    word |= byte << (8u * (i & 3u));
+    if ((i & 3u) == 3u) {
+      if (lane == 0) *reinterpret_cast<uint32_t *>(dst + (i - 3u)) = word;
+      word = 0;
+    }
+  }
+  if (lane == 0)
+    for (uint32_t b = 0; b < (n & 3u); b++) dst[(n & ~3u) + b] = (uint8_t)(word >> (8u * b));
+}
+
+/* ------------------------------------------------------------------------ */
+/* stream compaction: offsets = exclusive scan of lens, then a packed copy   */
+
+__global__ void w3_k_scan_lens(const uint32_t *__restrict__ lens, uint32_t n_blocks,
+                               uint64_t *__restrict__ offsets) {
+  __shared__ uint64_t part[1024];
+  const uint32_t tid = threadIdx.x, nt = blockDim.x;
+  const uint32_t per = (n_blocks + nt - 1) / nt;
+  const uint32_t lo = tid * per, hi = lo + per < n_blocks ? lo + per : n_blocks;
+  uint64_t sum = 0;
+  for (uint32_t i = lo; i < hi; i++) sum += lens[i];
+  part[tid] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    uint64_t run = 0;
+    for (uint32_t i = 0; i < nt; i++) { uint64_t v = part[i]; part[i] = run; run += v; }
+    offsets[n_blocks] = run;
+  }
+  __syncthreads();
+  uint64_t run = part[tid];
+  for (uint32_t i = lo; i < hi; i++) { offsets[i] = run; run += lens[i]; }
+}
+
+__global__ void w3_k_pack(const uint8_t *__restrict__ scratch, uint64_t stride,
+                          const uint64_t *__restrict__ offsets, uint8_t *__restrict__ packed) {
+  const uint32_t blk = blockIdx.x;
+  const uint64_t len = offsets[blk + 1] - offsets[blk];
+  const uint8_t *src = scratch + (uint64_t)blk * stride;
+  uint8_t *dst = packed + offsets[blk];
+  for (uint64_t i = (uint64_t)blockIdx.y * blockDim.x + threadIdx.x; i < len;
+       i += (uint64_t)gridDim.y * blockDim.x)
+    dst[i] = src[i];
+}
+
+/* ------------------------------------------------------------------------ */
+/* self-test kernels (called through w3_selftest_* in the C ABI by tests/)   */
+
+__global__ void w3_k_hash_array(const uint64_t *bits, const uint32_t *pos, uint32_t n,
+                                uint32_t *out, const w3_hashtab *tab) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  w3_smem_tab *st = reinterpret_cast<w3_smem_tab *>(smem_raw);
+  w3_load_tab(st, tab);
+  __syncthreads();
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    out[i] = w3_hash_dev(st, w3_key_of_history(bits[i]), pos[i]);
+}
+
+/* exhaustive Counter::p check: float estimate + fix-up vs the u64 statement */
+__global__ void w3_k_counter_p_check(unsigned long long *mismatches) {
+  const uint32_t c0 = blockIdx.x; /* 0..65534 */
+  unsigned long long bad = 0;
+  for (uint32_t c1 = threadIdx.x; c1 <= 65534u; c1 += blockDim.x)
+    bad += w3_counter_p(c0, c1) != w3_counter_p_u64(c0, c1);
+  if (bad) atomicAdd(mismatches, bad);
+}
+
+/* the coder alone with caller-supplied probabilities (the reference's KAT
+ * harness, arithmetic_coder_tests.rs:8-42), one thread.  Handles prob == 0 /
+ * x1 == x2 (32 shifts), which the codec kernels never meet. */
+__global__ void w3_k_ac_encode_probs(const uint8_t *in, const uint16_t *probs, uint32_t n_probs,
+                                     uint8_t *out, uint32_t cap, uint32_t *out_len) {
+  if (threadIdx.x || blockIdx.x) return;
+  uint32_t x1 = 0, x2 = 0xFFFFFFFFu;
+  w3_writer wr;
+  w3_writer_init(wr);
+  auto store = [&](uint32_t idx, uint32_t v) {
+    for (int b = 0; b < 4; b++)
+      if (idx * 4u + b < cap) out[idx * 4u + b] = (uint8_t)(v >> (24 - 8 * b));
+  };
+  for (uint32_t i = 0; i < n_probs; i++) {
+    uint32_t bit = (in[i >> 3] >> (7u - (i & 7u))) & 1u;
+    w3_ac_narrow(x1, x2, bit, w3_prob32(probs[i]));
+    uint32_t pre = x1;
+    int s, k;
+    if (x1 == x2) { s = 32; k = 0; x1 = 0; x2 = 0xFFFFFFFFu; }
+    else w3_ac_renorm(x1, x2, s, k);
+    w3_writer_step(wr, pre, s, k, store);
+  }
+  uint32_t tail, tb;
+  uint64_t len = w3_writer_flush(wr, x2, tail, tb, store);
+  for (uint32_t b = 0; b < tb; b++)
+    if (wr.words * 4u + b < cap) out[wr.words * 4u + b] = (uint8_t)(tail >> (24 - 8 * b));
+  *out_len = (uint32_t)len;
+}
+
+__global__ void w3_k_ac_decode_probs(const uint8_t *in, uint32_t n_in, const uint16_t *probs,
+                                     uint32_t n_probs, uint8_t *out) {
+  if (threadIdx.x || blockIdx.x) return;
+  w3_reader rd;
+  w3_reader_init(rd, in, n_in);
+  uint32_t x1 = 0, x2 = 0xFFFFFFFFu, x = w3_reader_take(rd, 32);
+  for (uint32_t i = 0; i < n_probs; i++) {
+    uint32_t xmid = x1 + __umulhi(x2 - x1, w3_prob32(probs[i]));
+    uint32_t bit = x <= xmid ? 1u : 0u;
+    if (bit) x2 = xmid; else x1 = xmid + 1u;
+    if (x1 == x2) { x1 = 0; x2 = 0xFFFFFFFFu; x = w3_reader_take(rd, 32); }
+    else {
+      int s, k;
+      int nsh = w3_ac_renorm(x1, x2, s, k);
+      if (nsh) x = ((x << nsh) | w3_reader_take(rd, nsh)) ^ (k ? 0x80000000u : 0u);
+    }
+    if ((i & 7u) == 0) out[i >> 3] = 0;
+    out[i >> 3] |= (uint8_t)(bit << (7u - (i & 7u)));
+  }
+}
+
+/* ------------------------------------------------------------------------ */
+/* launchers                                                                */
+
+static inline size_t w3_smem_bytes(int warps) {
+  return sizeof(w3_smem_tab) + (size_t)warps * W3_NCTX * sizeof(uint32_t);
+}
+
+/* warps per CTA: spread blocks over all 148 SMs first, then stack warps */
+static inline int w3_pick_warps(uint32_t n_blocks, int sm_count) {
+  int w = (int)((n_blocks + (uint32_t)sm_count - 1) / (uint32_t)sm_count);
+  if (w < 1) w = 1;
+  if (w > W3_MAX_WARPS) w = W3_MAX_WARPS;
+  return w;
+}
+
+extern "C" {
+
+cudaError_t w3_launch_build_table(w3_hashtab *d_tab, cudaStream_t s) {
+  w3_k_build_thr<<<8, 256, 0, s>>>(d_tab);
+  w3_k_build_cell_rval<<<(8 * W3_NCELL + 255) / 256, 256, 0, s>>>(d_tab);
+  return cudaGetLastError();
+}
+
+cudaError_t w3_kernels_init(void) {
+  cudaError_t e;
+  size_t mx = w3_smem_bytes(W3_MAX_WARPS);
+  e = cudaFuncSetAttribute(w3_encode_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(w3_decode_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(w3_k_hash_array, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)sizeof(w3_smem_tab));
+}
+
+cudaError_t w3_launch_encode(const uint8_t *d_in, uint64_t n_total, uint32_t block_size,
+                             uint32_t n_blocks, uint8_t *d_scratch, uint64_t stride,
+                             uint32_t *d_lens, uint32_t *d_overflow, const w3_hashtab *d_tab,
+                             int sm_count, cudaStream_t s) {
+  if (!n_blocks) return cudaSuccess;
+  int warps = w3_pick_warps(n_blocks, sm_count);
+  uint32_t grid = (n_blocks + (uint32_t)warps - 1) / (uint32_t)warps;
+  w3_encode_blocks<<<grid, warps * 32, w3_smem_bytes(warps), s>>>(
+      d_in, n_total, block_size, n_blocks, d_scratch, stride, d_lens, d_overflow, d_tab);
+  return cudaGetLastError();
+}
+
+cudaError_t w3_launch_pack(const uint8_t *d_scratch, uint64_t stride, const uint32_t *d_lens,
+                           uint32_t n_blocks, uint64_t *d_offsets, uint8_t *d_packed,
+                           cudaStream_t s) {
+  w3_k_scan_lens<<<1, 1024, 0, s>>>(d_lens, n_blocks, d_offsets);
+  if (n_blocks) {
+    dim3 grid(n_blocks, 32);
+    w3_k_pack<<<grid, 256, 0, s>>>(d_scratch, stride, d_offsets, d_packed);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t w3_launch_scan(const uint32_t *d_lens, uint32_t n_blocks, uint64_t *d_offsets,
+                           cudaStream_t s) {
+  w3_k_scan_lens<<<1, 1024, 0, s>>>(d_lens, n_blocks, d_offsets);
+  return cudaGetLastError();
+}
+
+cudaError_t w3_launch_decode(const uint8_t *d_comp, const uint64_t *d_offsets, uint32_t n_blocks,
+                             uint32_t block_size, uint64_t n_total, uint8_t *d_out,
+                             const w3_hashtab *d_tab, int sm_count, cudaStream_t s) {
+  if (!n_blocks) return cudaSuccess;
+  int warps = w3_pick_warps(n_blocks, sm_count);
+  uint32_t grid = (n_blocks + (uint32_t)warps - 1) / (uint32_t)warps;
+  w3_decode_blocks<<<grid, warps * 32, w3_smem_bytes(warps), s>>>(
+      d_comp, d_offsets, n_blocks, block_size, n_total, d_out, d_tab);
+  return cudaGetLastError();
+}
+
+cudaError_t w3_launch_hash_array(const uint64_t *d_bits, const uint32_t *d_pos, uint32_t n,
+                                 uint32_t *d_out, const w3_hashtab *d_tab, cudaStream_t s) {
+  w3_k_hash_array<<<64, 256, sizeof(w3_smem_tab), s>>>(d_bits, d_pos, n, d_out, d_tab);
+  return cudaGetLastError();
+}
+cudaError_t w3_launch_counter_p_check(unsigned long long *d_mismatches, cudaStream_t s) {
+  w3_k_counter_p_check<<<65535, 256, 0, s>>>(d_mismatches);
+  return cudaGetLastError();
+}
+cudaError_t w3_launch_ac_encode_probs(const uint8_t *d_in, const uint16_t *d_probs,
+                                      uint32_t n_probs, uint8_t *d_out, uint32_t cap,
+                                      uint32_t *d_out_len, cudaStream_t s) {
+  w3_k_ac_encode_probs<<<1, 32, 0, s>>>(d_in, d_probs, n_probs, d_out, cap, d_out_len);
+  return cudaGetLastError();
+}
+cudaError_t w3_launch_ac_decode_probs(const uint8_t *d_in, uint32_t n_in, const uint16_t *d_probs,
+                                      uint32_t n_probs, uint8_t *d_out, cudaStream_t s) {
+  w3_k_ac_decode_probs<<<1, 32, 0, s>>>(d_in, n_in, d_probs, n_probs, d_out);
+  return cudaGetLastError();
+}
+
+} /* extern "C" */

@@ -1,0 +1,37 @@
+/* w3_kernels.h — internal launchers (w3_kernels.cu) used by the C ABI (w3_capi.cu). */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define W3_MAX_WARPS 8 /* blocks (= warps) sharing one CTA's copy of the threshold table */
+
+struct w3_hashtab;
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+cudaError_t w3_kernels_init(void);
+cudaError_t w3_launch_build_table(struct w3_hashtab *d_tab, cudaStream_t s);
+cudaError_t w3_launch_encode(const uint8_t *d_in, uint64_t n_total, uint32_t block_size,
+                             uint32_t n_blocks, uint8_t *d_scratch, uint64_t stride,
+                             uint32_t *d_lens, uint32_t *d_overflow,
+                             const struct w3_hashtab *d_tab, int sm_count, cudaStream_t s);
+cudaError_t w3_launch_scan(const uint32_t *d_lens, uint32_t n_blocks, uint64_t *d_offsets,
+                           cudaStream_t s);
+cudaError_t w3_launch_pack(const uint8_t *d_scratch, uint64_t stride, const uint32_t *d_lens,
+                           uint32_t n_blocks, uint64_t *d_offsets, uint8_t *d_packed,
+                           cudaStream_t s);
+cudaError_t w3_launch_decode(const uint8_t *d_comp, const uint64_t *d_offsets, uint32_t n_blocks,
+                             uint32_t block_size, uint64_t n_total, uint8_t *d_out,
+                             const struct w3_hashtab *d_tab, int sm_count, cudaStream_t s);
+cudaError_t w3_launch_hash_array(const uint64_t *d_bits, const uint32_t *d_pos, uint32_t n,
+                                 uint32_t *d_out, const struct w3_hashtab *d_tab, cudaStream_t s);
+cudaError_t w3_launch_counter_p_check(unsigned long long *d_mismatches, cudaStream_t s);
+cudaError_t w3_launch_ac_encode_probs(const uint8_t *d_in, const uint16_t *d_probs,
+                                      uint32_t n_probs, uint8_t *d_out, uint32_t cap,
+                                      uint32_t *d_out_len, cudaStream_t s);
+cudaError_t w3_launch_ac_decode_probs(const uint8_t *d_in, uint32_t n_in, const uint16_t *d_probs,
+                                      uint32_t n_probs, uint8_t *d_out, cudaStream_t s);
+#ifdef __cplusplus
+}
+#endif
