@@ -200,7 +200,7 @@ def run_b200(args):
                         d_packed.data_ptr(), stream)
         if timed:
             e[2].record()
-        ctx.decode_device(d_packed.data_ptr(), d_offs.data_ptr(), n_blocks, block, n, d_out.data_ptr(), stream)
+        ctx.decode_device(d_packed.data_ptr(), d_offs.data_ptr(), n_blocks, block, n, d_out.data_ptr(), d_flag.data_ptr(), stream)
         if timed:
             e[3].record()
         return e
@@ -214,7 +214,7 @@ def run_b200(args):
     for _ in range(args.warmup):
         step(False)
     barrier()
-    assert int(d_flag.item()) == 0, "scratch overflow"
+    assert int(d_flag.item()) == 0, "scratch overflow or kernel abort"
     assert torch.equal(d_out[:n], d_in[:n]), "device round trip mismatch"
     comp_bytes = int(d_offs[n_blocks].item())
 

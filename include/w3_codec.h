@@ -77,8 +77,8 @@ int w3_decompressed_size(const uint8_t *in, size_t n_in, size_t *out_len);
 
 /* Encodes n_blocks = ceil(n / block_size) blocks from d_in into per-block
  * scratch regions d_scratch + i * stride (stride a multiple of 4);
- * d_lens[i] = stream length; *d_overflow != 0 afterwards if any stream did not
- * fit its region.  d_in must be readable up to the next multiple of 4. */
+ * d_lens[i] = stream length; afterwards *d_overflow has bit 0 set if any stream
+ * did not fit its region (bit 1: a kernel gave up, never expected).  d_in must be readable up to the next multiple of 4. */
 int w3_encode_device(w3_ctx *ctx, int dev, const void *d_in, size_t n, size_t block_size,
                      void *d_scratch, size_t stride, uint32_t *d_lens, uint32_t *d_overflow,
                      void *stream);
@@ -88,9 +88,12 @@ int w3_pack_device(w3_ctx *ctx, int dev, const void *d_scratch, size_t stride,
                    const uint32_t *d_lens, size_t n_blocks, uint64_t *d_offsets, void *d_packed,
                    void *stream);
 /* Decodes streams d_comp + d_offsets[i] .. d_offsets[i+1] into d_out (n bytes
- * total, block i at i * block_size).  d_comp needs 8 readable bytes of slack. */
+ * total, block i at i * block_size).  d_comp needs 8 readable bytes of slack.
+ * *d_err (device word, may be NULL) is OR-ed with a non-zero code if a kernel
+ * gave up (never expected; a bounded inter-warp wait timed out). */
 int w3_decode_device(w3_ctx *ctx, int dev, const void *d_comp, const uint64_t *d_offsets,
-                     size_t n_blocks, size_t block_size, size_t n, void *d_out, void *stream);
+                     size_t n_blocks, size_t block_size, size_t n, void *d_out, uint32_t *d_err,
+                     void *stream);
 
 /* ---- self-tests of single stages, used by tests/ -------------------------- */
 /* ACHistory::hash (src/history/ac_history.rs:28-46) for n (bits,pos) pairs, host arrays */

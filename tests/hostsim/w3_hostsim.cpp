@@ -38,7 +38,7 @@ uint32_t hs_hash_exact(uint64_t bits, uint32_t pos, const uint16_t *table, int m
 /* table lookup with the exact fallback, as the kernels do it */
 uint32_t hs_hash(const w3_hashtab *tab, uint64_t bits, uint32_t pos, int *slow) {
   uint32_t h = w3_hash_lookup(w3_key_of_history(bits), pos & 7u, &tab->thr[0][0],
-                              &tab->cell[0][0], &tab->rval[0][0]);
+                              &tab->cell[0][0]);
   if (slow) *slow = h == 0xFFFFFFFFu;
   if (h == 0xFFFFFFFFu) h = w3_achash_exact(bits, pos, tab->table, tab->max_bits).hash;
   return h;

@@ -20,6 +20,14 @@ def ctx():
     c.close()
 
 
+@pytest.fixture(params=["team", "warp"], autouse=True)
+def kernel_mode(request, monkeypatch):
+    """Every test runs against both kernel families: `team` (one CTA per block,
+    coder warp + model/speculator warps) and `warp` (one warp per block)."""
+    monkeypatch.setenv("W3_MODE", request.param)
+    return request.param
+
+
 def split_container(blob):
     assert blob[:4] == b"w3Bk" and blob[4] == 1
     n = int.from_bytes(blob[8:16], "big")

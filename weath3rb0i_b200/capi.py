@@ -60,7 +60,7 @@ def load():
     lib.w3_decompressed_size.argtypes = [u8p, sz, C.POINTER(sz)]
     lib.w3_encode_device.argtypes = [vp, C.c_int, vp, sz, sz, vp, sz, vp, vp, vp]
     lib.w3_pack_device.argtypes = [vp, C.c_int, vp, sz, vp, sz, vp, vp, vp]
-    lib.w3_decode_device.argtypes = [vp, C.c_int, vp, vp, sz, sz, sz, vp, vp]
+    lib.w3_decode_device.argtypes = [vp, C.c_int, vp, vp, sz, sz, sz, vp, vp, vp]
     lib.w3_selftest_achash.argtypes = [vp, vp, vp, sz, vp]
     lib.w3_selftest_counter_p.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.w3_selftest_ac_encode.argtypes = [vp, u8p, sz, vp, sz, u8p, sz, C.POINTER(sz)]
@@ -164,9 +164,9 @@ class Context:
         check(self.lib.w3_pack_device(self.handle, dev, d_scratch, stride, d_lens, n_blocks,
                                       d_offsets, d_packed, stream))
 
-    def decode_device(self, d_comp, d_offsets, n_blocks, block_size, n, d_out, stream=0, dev=0):
+    def decode_device(self, d_comp, d_offsets, n_blocks, block_size, n, d_out, d_err=None, stream=0, dev=0):
         check(self.lib.w3_decode_device(self.handle, dev, d_comp, d_offsets, n_blocks, block_size,
-                                        n, d_out, stream))
+                                        n, d_out, d_err, stream))
 
     # ---- stage self-tests ------------------------------------------------
     def achash(self, bits, pos):

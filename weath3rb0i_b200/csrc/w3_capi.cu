@@ -221,7 +221,8 @@ int w3_pack_device(w3_ctx *ctx, int dev, const void *d_scratch, size_t stride,
 }
 
 int w3_decode_device(w3_ctx *ctx, int dev, const void *d_comp, const uint64_t *d_offsets,
-                     size_t n_blocks, size_t block_size, size_t n, void *d_out, void *stream) {
+                     size_t n_blocks, size_t block_size, size_t n, void *d_out, uint32_t *d_err,
+                     void *stream) {
   if (!ctx || dev < 0 || dev >= ctx->n || !block_size || (block_size & 3) || block_size > MAX_BLOCK)
     return W3_E_ARG;
   if (n_blocks != (n + block_size - 1) / block_size || n_blocks > 0xFFFFFFFFull) return W3_E_ARG;
@@ -230,7 +231,8 @@ int w3_decode_device(w3_ctx *ctx, int dev, const void *d_comp, const uint64_t *d
   w3_dev &d = ctx->d[dev];
   CK(cudaSetDevice(d.ordinal));
   CK(w3_launch_decode((const uint8_t *)d_comp, d_offsets, (uint32_t)n_blocks, (uint32_t)block_size,
-                      n, (uint8_t *)d_out, d.d_tab, d.sm_count, (cudaStream_t)stream));
+                      n, (uint8_t *)d_out, d_err ? d_err : d.d_flag, d.d_tab, d.sm_count,
+                      (cudaStream_t)stream));
   return W3_OK;
 }
 
@@ -271,6 +273,7 @@ static int encode_part(w3_ctx *ctx, int g, const uint8_t *in, size_t n, size_t b
     CK(cudaMemcpyAsync(&flag, d.d_flag, 4, cudaMemcpyDeviceToHost, d.stream));
     CK(cudaMemcpyAsync(part.lens.data(), d.lens.p, nb * 4, cudaMemcpyDeviceToHost, d.stream));
     CK(cudaStreamSynchronize(d.stream));
+    if (flag & 2u) { snprintf(g_cuda_err, sizeof g_cuda_err, "encode kernel aborted (inter-warp wait timed out)"); return W3_E_CUDA; }
     if (!flag) break;
     if (attempt) { snprintf(g_cuda_err, sizeof g_cuda_err, "stream exceeded the 17n bound"); return W3_E_CUDA; }
     stride = round_up(17 * bs + 64, 16);
@@ -405,10 +408,15 @@ int w3_decompress(w3_ctx *ctx, const uint8_t *in, size_t n_in, uint8_t *out, siz
     CK(cudaMemsetAsync((uint8_t *)d.packed.p + clen, 0, 16, d.stream));
     if (clen) CK(cudaMemcpyAsync(d.packed.p, in + hdr + c0, clen, cudaMemcpyHostToDevice, d.stream));
     CK(cudaMemcpyAsync(d.offsets.p, rel.data(), (nbg + 1) * 8, cudaMemcpyHostToDevice, d.stream));
+    CK(cudaMemsetAsync(d.d_flag, 0, 4, d.stream));
     CK(w3_launch_decode((const uint8_t *)d.packed.p, (const uint64_t *)d.offsets.p, (uint32_t)nbg,
-                        (uint32_t)bs, obytes, (uint8_t *)d.out.p, d.d_tab, d.sm_count, d.stream));
+                        (uint32_t)bs, obytes, (uint8_t *)d.out.p, d.d_flag, d.d_tab, d.sm_count,
+                        d.stream));
+    uint32_t flag = 0;
+    CK(cudaMemcpyAsync(&flag, d.d_flag, 4, cudaMemcpyDeviceToHost, d.stream));
     CK(cudaMemcpyAsync(out + o0, d.out.p, obytes, cudaMemcpyDeviceToHost, d.stream));
     CK(cudaStreamSynchronize(d.stream));
+    if (flag) { snprintf(g_cuda_err, sizeof g_cuda_err, "decode kernel aborted (flag %u)", flag); return (int)W3_E_CUDA; }
     return (int)W3_OK;
   });
 }

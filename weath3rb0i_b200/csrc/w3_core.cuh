@@ -91,13 +91,14 @@ W3_HD void w3_ac_narrow(uint32_t &x1, uint32_t &x2, uint32_t bit, uint32_t P) {
  * shifts (bits to emit / read plainly), k = E3 shifts; returns s + k <= 31. */
 W3_HD int w3_ac_renorm(uint32_t &x1, uint32_t &x2, int &s, int &k) {
   s = w3_clz32(x1 ^ x2);
-  uint32_t h = ((~x1 | x2) << s) << 1; /* 0-bits = (1,0) pairs below the split */
-  int kk = w3_clz32(h);
-  int lim = 31 - s;
-  k = kk < lim ? kk : lim;
+  /* 0-bits of (~x1 | x2) are (1,0) pairs; after dropping the s equal pairs and
+   * the first differing one, the leading zero run is the E3 count.  The `| 1`
+   * lands on bit s after the shift and caps the run at the word's end. */
+  uint32_t h = (((~x1 | x2) << 1) | 1u) << s;
+  k = w3_clz32(h);
   int n = s + k;
   x1 = (x1 << n) & 0x7FFFFFFFu;
-  x2 = (x2 << n) | ((1u << n) - 1u) | 0x80000000u;
+  x2 = (x2 << n) | ~(0xFFFFFFFFu << n) | 0x80000000u;
   return n;
 }
 
@@ -223,20 +224,23 @@ W3_HD uint64_t w3_threshold_search(uint32_t a, uint32_t j, const uint16_t *table
 
 /* Table form of ACHistory::hash.  `thr`, `cell`, `rval` may point to shared
  * memory copies.  Returns the hash, or 0xFFFFFFFF when the key equals a
- * threshold (possible singular key) and the caller must use w3_achash_exact. */
+ * threshold (possible singular key) and the caller must use w3_achash_exact.
+ * rval[][] of the global table is the same mapping evaluated with the literal
+ * loop; the builder cross-checks the two (w3_build_rval). */
 W3_HD uint32_t w3_hash_lookup(uint64_t key, uint32_t a, const uint64_t *thr /*[8][256]*/,
-                              const uint16_t *cell /*[8][NCELL]*/,
-                              const uint8_t *rval /*[8][256]*/) {
+                              const uint16_t *cell /*[8][NCELL]*/) {
   uint32_t e = cell[a * W3_NCELL + (uint32_t)(key >> (64 - W3_PB))];
   uint32_t r = e & 0xFFu, cnt = e >> 8;
   const uint64_t *t = thr + a * 256u + r;
   bool eq = false;
-  for (uint32_t i = 0; i < cnt; i++) {
+  for (uint32_t i = 0; i < cnt; i++) { /* independent loads: no early exit on purpose */
     uint64_t b = t[i];
     r += key >= b ? 1u : 0u;
     eq |= key == b;
   }
-  return eq ? 0xFFFFFFFFu : (uint32_t)rval[a * 256u + r];
+  if (eq) return 0xFFFFFFFFu;
+  /* region r holds code bin 255 - r; the hash is the code, first bit lowest */
+  return w3_brev32(255u - r) >> 24;
 }
 
 /* ---- bit writer (ACWriter — src/entropy_coding/io.rs:52-101) -------------- */
@@ -335,4 +339,5 @@ W3_HD void w3_build_rval(w3_hashtab *tab, uint32_t a, uint32_t r) {
       w3_key_rank2(lo, a, tab->table, tab->max_bits) != 2u * r)
     tab->bad = 1;
   tab->rval[a][r] = (uint8_t)h.hash;
+  if (h.hash != (w3_brev32(255u - r) >> 24)) tab->bad = 1; /* analytic form used by lookups */
 }

@@ -20,6 +20,8 @@
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "w3_core.cuh"
 #include "w3_kernels.h"
@@ -45,7 +47,6 @@ __global__ void w3_k_build_cell_rval(w3_hashtab *tab) {
 struct w3_smem_tab {
   uint64_t thr[8 * 256];
   uint16_t cell[8 * W3_NCELL];
-  uint8_t rval[8 * 256];
   uint16_t table[8];
   uint32_t max_bits;
   uint32_t pad[3];
@@ -60,16 +61,13 @@ __device__ __forceinline__ void w3_load_tab(w3_smem_tab *s, const w3_hashtab *g)
   const uint4 *gc = reinterpret_cast<const uint4 *>(&g->cell[0][0]);
   uint4 *sc = reinterpret_cast<uint4 *>(s->cell);
   for (uint32_t i = tid; i < sizeof(s->cell) / 16; i += nt) sc[i] = gc[i];
-  const uint4 *gr = reinterpret_cast<const uint4 *>(&g->rval[0][0]);
-  uint4 *sr = reinterpret_cast<uint4 *>(s->rval);
-  for (uint32_t i = tid; i < sizeof(s->rval) / 16; i += nt) sr[i] = gr[i];
   if (tid < 8) s->table[tid] = g->table[tid];
   if (tid == 0) s->max_bits = g->max_bits;
 }
 
 /* ACHistory::hash through the table, literal loop for threshold keys */
 __device__ __forceinline__ uint32_t w3_hash_dev(const w3_smem_tab *s, uint64_t key, uint32_t pos) {
-  uint32_t h = w3_hash_lookup(key, pos & 7u, s->thr, s->cell, s->rval);
+  uint32_t h = w3_hash_lookup(key, pos & 7u, s->thr, s->cell);
   if (h == 0xFFFFFFFFu)
     h = w3_achash_exact(w3_key_of_history(key), pos, s->table, (int)s->max_bits).hash;
   return h;
@@ -81,7 +79,7 @@ __device__ __forceinline__ uint32_t w3_bswap(uint32_t v) { return __byte_perm(v,
 /* encode: one warp per block                                               */
 
 __global__ void __launch_bounds__(W3_MAX_WARPS * 32)
-w3_encode_blocks(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t block_size,
+w3_encode_blocks_warp(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t block_size,
                  uint32_t n_blocks, uint8_t *__restrict__ scratch, uint64_t stride,
                  uint32_t *__restrict__ lens, uint32_t *__restrict__ overflow,
                  const w3_hashtab *__restrict__ tab) {
@@ -263,7 +261,7 @@ __device__ __forceinline__ uint32_t w3_reader_take(w3_reader &r, int c) { /* c i
 }
 
 __global__ void __launch_bounds__(W3_MAX_WARPS * 32)
-w3_decode_blocks(const uint8_t *__restrict__ comp, const uint64_t *__restrict__ offsets,
+w3_decode_blocks_warp(const uint8_t *__restrict__ comp, const uint64_t *__restrict__ offsets,
                  uint32_t n_blocks, uint32_t block_size, uint64_t n_total,
                  uint8_t *__restrict__ out, const w3_hashtab *__restrict__ tab) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -317,6 +315,8 @@ w3_decode_blocks(const uint8_t *__restrict__ comp, const uint64_t *__restrict__ 
   if (lane == 0)
     for (uint32_t b = 0; b < (n & 3u); b++) dst[(n & ~3u) + b] = (uint8_t)(word >> (8u * b));
 }
+
+#include "w3_team.cuh"
 
 /* ------------------------------------------------------------------------ */
 /* stream compaction: offsets = exclusive scan of lens, then a packed copy   */
@@ -439,6 +439,15 @@ static inline int w3_pick_warps(uint32_t n_blocks, int sm_count) {
   return w;
 }
 
+/* W3_MODE=warp|team overrides the choice; by default the team kernels run while
+ * every block's CTA can be resident at once (3 CTAs of ~66 KiB smem per SM) */
+static inline bool w3_use_team(uint32_t n_blocks, int sm_count) {
+  const char *m = getenv("W3_MODE");
+  if (m && !strcmp(m, "warp")) return false;
+  if (m && !strcmp(m, "team")) return true;
+  return n_blocks <= 3u * (uint32_t)sm_count;
+}
+
 extern "C" {
 
 cudaError_t w3_launch_build_table(w3_hashtab *d_tab, cudaStream_t s) {
@@ -450,9 +459,15 @@ cudaError_t w3_launch_build_table(w3_hashtab *d_tab, cudaStream_t s) {
 cudaError_t w3_kernels_init(void) {
   cudaError_t e;
   size_t mx = w3_smem_bytes(W3_MAX_WARPS);
-  e = cudaFuncSetAttribute(w3_encode_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx);
+  e = cudaFuncSetAttribute(w3_encode_blocks_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(w3_decode_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx);
+  e = cudaFuncSetAttribute(w3_decode_blocks_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(w3_encode_blocks_team, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(sizeof(w3_smem_tab) + sizeof(w3_enc_team)));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(w3_decode_blocks_team, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(sizeof(w3_smem_tab) + sizeof(w3_dec_team)));
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(w3_k_hash_array, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)sizeof(w3_smem_tab));
@@ -463,9 +478,14 @@ cudaError_t w3_launch_encode(const uint8_t *d_in, uint64_t n_total, uint32_t blo
                              uint32_t *d_lens, uint32_t *d_overflow, const w3_hashtab *d_tab,
                              int sm_count, cudaStream_t s) {
   if (!n_blocks) return cudaSuccess;
+  if (w3_use_team(n_blocks, sm_count)) {
+    w3_encode_blocks_team<<<n_blocks, 64, sizeof(w3_smem_tab) + sizeof(w3_enc_team), s>>>(
+        d_in, n_total, block_size, n_blocks, d_scratch, stride, d_lens, d_overflow, d_tab);
+    return cudaGetLastError();
+  }
   int warps = w3_pick_warps(n_blocks, sm_count);
   uint32_t grid = (n_blocks + (uint32_t)warps - 1) / (uint32_t)warps;
-  w3_encode_blocks<<<grid, warps * 32, w3_smem_bytes(warps), s>>>(
+  w3_encode_blocks_warp<<<grid, warps * 32, w3_smem_bytes(warps), s>>>(
       d_in, n_total, block_size, n_blocks, d_scratch, stride, d_lens, d_overflow, d_tab);
   return cudaGetLastError();
 }
@@ -489,11 +509,18 @@ cudaError_t w3_launch_scan(const uint32_t *d_lens, uint32_t n_blocks, uint64_t *
 
 cudaError_t w3_launch_decode(const uint8_t *d_comp, const uint64_t *d_offsets, uint32_t n_blocks,
                              uint32_t block_size, uint64_t n_total, uint8_t *d_out,
-                             const w3_hashtab *d_tab, int sm_count, cudaStream_t s) {
+                             uint32_t *d_err, const w3_hashtab *d_tab, int sm_count,
+                             cudaStream_t s) {
   if (!n_blocks) return cudaSuccess;
+  if (w3_use_team(n_blocks, sm_count)) {
+    w3_decode_blocks_team<<<n_blocks, W3_DEC_TEAM_THREADS,
+                            sizeof(w3_smem_tab) + sizeof(w3_dec_team), s>>>(
+        d_comp, d_offsets, n_blocks, block_size, n_total, d_out, d_err, d_tab);
+    return cudaGetLastError();
+  }
   int warps = w3_pick_warps(n_blocks, sm_count);
   uint32_t grid = (n_blocks + (uint32_t)warps - 1) / (uint32_t)warps;
-  w3_decode_blocks<<<grid, warps * 32, w3_smem_bytes(warps), s>>>(
+  w3_decode_blocks_warp<<<grid, warps * 32, w3_smem_bytes(warps), s>>>(
       d_comp, d_offsets, n_blocks, block_size, n_total, d_out, d_tab);
   return cudaGetLastError();
 }
