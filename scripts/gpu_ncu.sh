@@ -7,9 +7,9 @@ python bench.py $ARGS > gpurun_out/ncu_plain.json 2> gpurun_out/ncu_plain.err &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv python bench.py $ARGS > gpurun_out/ncu_launch.log 2>&1
 echo "launch list rc=$?"
 python bench.py $ARGS > gpurun_out/ncu_plain2.json 2>> gpurun_out/ncu_plain.err &&
-ncu --set full --clock-control none --import-source on -k regex:w3_encode_blocks -s 3 -c 1 -f -o gpurun_out/prof_encode python bench.py $ARGS > gpurun_out/ncu_enc.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:w3_encode_blocks_team -s 3 -c 1 -f -o gpurun_out/prof_encode python bench.py $ARGS > gpurun_out/ncu_enc.log 2>&1
 echo "enc rc=$?"
 python bench.py $ARGS > gpurun_out/ncu_plain3.json 2>> gpurun_out/ncu_plain.err &&
-ncu --set full --clock-control none --import-source on -k regex:w3_decode_blocks -s 3 -c 1 -f -o gpurun_out/prof_decode python bench.py $ARGS > gpurun_out/ncu_dec.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:w3_decode_blocks_team -s 3 -c 1 -f -o gpurun_out/prof_decode python bench.py $ARGS > gpurun_out/ncu_dec.log 2>&1
 echo "dec rc=$?"
 ls -la gpurun_out

@@ -44,6 +44,13 @@ uint32_t hs_hash(const w3_hashtab *tab, uint64_t bits, uint32_t pos, int *slow) 
   return h;
 }
 
+/* the relabelled context the kernels use: (rank << 3) | alignment */
+static uint32_t ranked_ctx(const w3_hashtab *tab, uint64_t bits, uint32_t pos) {
+  uint32_t r = w3_rank_lookup(w3_key_of_history(bits), pos & 7u, &tab->thr[0][0], &tab->cell[0][0]);
+  if (r == 0xFFFFFFFFu) r = w3_rank_of_hash(w3_achash_exact(bits, pos, tab->table, tab->max_bits).hash);
+  return (r << 3) | (pos & 7u);
+}
+
 /* number of thresholds compared for this key (cell occupancy statistics) */
 uint32_t hs_cell_count(const w3_hashtab *tab, uint64_t bits, uint32_t pos) {
   uint64_t key = w3_key_of_history(bits);
@@ -61,10 +68,13 @@ uint64_t hs_counter_p_sweep(uint32_t c0_lo, uint32_t c0_hi, uint32_t step) {
 uint32_t hs_counter_update(uint32_t slot, uint32_t bit) { return w3_counter_update(slot, bit); }
 
 /* scalar encode of one block, built only from w3_core.cuh statements */
+static int g_ranked = 0; /* 1: index counters by rank, as the kernels do */
+void hs_set_ranked(int on) { g_ranked = on; }
+
 int hs_compress_block(const w3_hashtab *tab, const uint8_t *in, size_t n, uint8_t *out, size_t cap,
                       size_t *out_len) {
   std::vector<uint32_t> stats(W3_NCTX, 0u);
-  uint32_t x1 = 0, x2 = 0xFFFFFFFFu, ctx = 0;
+  uint32_t x1 = 0, x2 = 0xFFFFFFFFu, ctx = g_ranked ? W3_CTX0_RANKED : 0;
   uint64_t hist = 0;
   w3_writer w;
   w3_writer_init(w);
@@ -81,7 +91,8 @@ int hs_compress_block(const w3_hashtab *tab, const uint8_t *in, size_t n, uint8_
       stats[ctx] = w3_counter_update(slot, bit);
       hist = (hist << 1) | bit;
       t++;
-      ctx = (hs_hash(tab, hist, (uint32_t)t, nullptr) << 3) | (uint32_t)(t & 7u);
+      ctx = g_ranked ? ranked_ctx(tab, hist, (uint32_t)t)
+                     : (hs_hash(tab, hist, (uint32_t)t, nullptr) << 3) | (uint32_t)(t & 7u);
       w3_ac_narrow(x1, x2, bit, w3_prob32(p));
       uint32_t pre = x1;
       int s, k;
@@ -100,7 +111,7 @@ int hs_compress_block(const w3_hashtab *tab, const uint8_t *in, size_t n, uint8_
 int hs_decompress_block(const w3_hashtab *tab, const uint8_t *in, size_t n_in, uint8_t *out,
                         size_t n_out) {
   std::vector<uint32_t> stats(W3_NCTX, 0u);
-  uint32_t x1 = 0, x2 = 0xFFFFFFFFu, ctx = 0;
+  uint32_t x1 = 0, x2 = 0xFFFFFFFFu, ctx = g_ranked ? W3_CTX0_RANKED : 0;
   uint64_t hist = 0, t = 0;
   size_t bitpos = 0;
   auto take = [&](int c) -> uint32_t {
@@ -128,7 +139,8 @@ int hs_decompress_block(const w3_hashtab *tab, const uint8_t *in, size_t n_in, u
       stats[ctx] = w3_counter_update(slot, bit);
       hist = (hist << 1) | bit;
       t++;
-      ctx = (hs_hash(tab, hist, (uint32_t)t, nullptr) << 3) | (uint32_t)(t & 7u);
+      ctx = g_ranked ? ranked_ctx(tab, hist, (uint32_t)t)
+                     : (hs_hash(tab, hist, (uint32_t)t, nullptr) << 3) | (uint32_t)(t & 7u);
       byte = (byte << 1) | bit;
     }
     out[i] = (uint8_t)byte;

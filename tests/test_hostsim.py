@@ -115,3 +115,19 @@ def test_counter_halving_reached(libs):
     c = libs.hostsim.compress_block(data)
     assert c == libs.oracle.compress_block(data)
     assert libs.hostsim.decompress_block(c, len(data)) == data
+
+
+def test_rank_relabelled_counters_change_nothing(libs):
+    """The kernels index the counter table by (rank << 3) | alignment, a
+    bijective relabelling of (hash << 3) | alignment: same bytes out."""
+    rnd = random.Random(13)
+    cases = [w3_corpus.generate(50000, offset=5), bytes(rnd.getrandbits(8) for _ in range(20000)),
+             b"e" * 70000, bytes(3000), b""]
+    libs.hostsim.lib.hs_set_ranked(1)
+    try:
+        for data in cases:
+            c = libs.hostsim.compress_block(data)
+            assert c == libs.oracle.compress_block(data)
+            assert libs.hostsim.decompress_block(c, len(data)) == data
+    finally:
+        libs.hostsim.lib.hs_set_ranked(0)

@@ -52,6 +52,16 @@ W3_HD int w3_clz32(uint32_t v) {
   return v ? __builtin_clz(v) : 32;
 #endif
 }
+/* clz for a non-zero word: one FLO.U32.SH on the device */
+W3_HD int w3_clz32_nz(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  uint32_t r;
+  asm("bfind.shiftamt.u32 %0, %1;" : "=r"(r) : "r"(v));
+  return (int)r;
+#else
+  return __builtin_clz(v);
+#endif
+}
 W3_HD uint32_t w3_umulhi(uint32_t a, uint32_t b) {
 #if defined(__CUDA_ARCH__)
   return __umulhi(a, b);
@@ -90,12 +100,12 @@ W3_HD void w3_ac_narrow(uint32_t &x1, uint32_t &x2, uint32_t bit, uint32_t P) {
  * see DESIGN.md).  On return x1/x2 are renormalised, s = matching-prefix
  * shifts (bits to emit / read plainly), k = E3 shifts; returns s + k <= 31. */
 W3_HD int w3_ac_renorm(uint32_t &x1, uint32_t &x2, int &s, int &k) {
-  s = w3_clz32(x1 ^ x2);
+  s = w3_clz32_nz(x1 ^ x2);
   /* 0-bits of (~x1 | x2) are (1,0) pairs; after dropping the s equal pairs and
    * the first differing one, the leading zero run is the E3 count.  The `| 1`
    * lands on bit s after the shift and caps the run at the word's end. */
   uint32_t h = (((~x1 | x2) << 1) | 1u) << s;
-  k = w3_clz32(h);
+  k = w3_clz32_nz(h);
   int n = s + k;
   x1 = (x1 << n) & 0x7FFFFFFFu;
   x2 = (x2 << n) | ~(0xFFFFFFFFu << n) | 0x80000000u;
@@ -107,7 +117,9 @@ W3_HD int w3_ac_renorm(uint32_t &x1, uint32_t &x2, int &s, int &k) {
 W3_HD uint32_t w3_counter_p(uint32_t c0, uint32_t c1) {
   uint32_t a = c1 + 1u, d = c0 + c1 + 2u;
 #if defined(__CUDA_ARCH__)
-  uint32_t q = (uint32_t)__fdividef((float)a * 131072.0f, (float)d);
+  float rcp; /* d >= 2: no denormal or overflow case to guard */
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"((float)d));
+  uint32_t q = (uint32_t)((float)a * 131072.0f * rcp);
 #else
   uint32_t q = (uint32_t)((float)a * 131072.0f / (float)d);
 #endif
@@ -222,12 +234,14 @@ W3_HD uint64_t w3_threshold_search(uint32_t a, uint32_t j, const uint16_t *table
   return lo;
 }
 
-/* Table form of ACHistory::hash.  `thr`, `cell`, `rval` may point to shared
- * memory copies.  Returns the hash, or 0xFFFFFFFF when the key equals a
- * threshold (possible singular key) and the caller must use w3_achash_exact.
+/* Table form of ACHistory::hash.  `thr`, `cell` may point to shared-memory
+ * copies.  Returns the RANK r = #{thresholds <= key} (0..255): region r holds
+ * code bin 255 - r and the hash is that code with its first bit lowest, i.e.
+ * hash = brev8(255 - r).  Returns 0xFFFFFFFF when the key equals a threshold
+ * (possible singular key): the caller must then use w3_achash_exact.
  * rval[][] of the global table is the same mapping evaluated with the literal
  * loop; the builder cross-checks the two (w3_build_rval). */
-W3_HD uint32_t w3_hash_lookup(uint64_t key, uint32_t a, const uint64_t *thr /*[8][256]*/,
+W3_HD uint32_t w3_rank_lookup(uint64_t key, uint32_t a, const uint64_t *thr /*[8][256]*/,
                               const uint16_t *cell /*[8][NCELL]*/) {
   uint32_t e = cell[a * W3_NCELL + (uint32_t)(key >> (64 - W3_PB))];
   uint32_t r = e & 0xFFu, cnt = e >> 8;
@@ -238,10 +252,22 @@ W3_HD uint32_t w3_hash_lookup(uint64_t key, uint32_t a, const uint64_t *thr /*[8
     r += key >= b ? 1u : 0u;
     eq |= key == b;
   }
-  if (eq) return 0xFFFFFFFFu;
-  /* region r holds code bin 255 - r; the hash is the code, first bit lowest */
-  return w3_brev32(255u - r) >> 24;
+  return eq ? 0xFFFFFFFFu : r;
 }
+W3_HD uint32_t w3_hash_of_rank(uint32_t r) { return w3_brev32(255u - r) >> 24; }
+W3_HD uint32_t w3_rank_of_hash(uint32_t h) { return 255u - (w3_brev32(h) >> 24); }
+W3_HD uint32_t w3_hash_lookup(uint64_t key, uint32_t a, const uint64_t *thr, const uint16_t *cell) {
+  uint32_t r = w3_rank_lookup(key, a, thr, cell);
+  return r == 0xFFFFFFFFu ? r : w3_hash_of_rank(r);
+}
+
+/* The kernels index the counter table by (rank << 3) | alignment instead of
+ * (hash << 3) | alignment (ordern_entropy.rs:43-44).  rank <-> hash is a
+ * bijection on 0..255 and the table is private to a block and starts at zero,
+ * so this only relabels the 2048 counters: every predicted probability, hence
+ * every output byte, is unchanged (tests/test_hostsim.py checks it against the
+ * oracle).  ctx_0 = 0 (ordern_entropy.rs:20) is hash 0, alignment 0. */
+#define W3_CTX0_RANKED (255u << W3_ALIGN_BITS)
 
 /* ---- bit writer (ACWriter — src/entropy_coding/io.rs:52-101) -------------- */
 /* Words are assembled MSB-first in a 64-bit accumulator and stored as

@@ -65,12 +65,13 @@ __device__ __forceinline__ void w3_load_tab(w3_smem_tab *s, const w3_hashtab *g)
   if (tid == 0) s->max_bits = g->max_bits;
 }
 
-/* ACHistory::hash through the table, literal loop for threshold keys */
-__device__ __forceinline__ uint32_t w3_hash_dev(const w3_smem_tab *s, uint64_t key, uint32_t pos) {
-  uint32_t h = w3_hash_lookup(key, pos & 7u, s->thr, s->cell);
-  if (h == 0xFFFFFFFFu)
-    h = w3_achash_exact(w3_key_of_history(key), pos, s->table, (int)s->max_bits).hash;
-  return h;
+/* ACHistory::hash through the table, as a rank (see w3_rank_lookup); the
+ * literal loop handles keys that sit exactly on a threshold */
+__device__ __forceinline__ uint32_t w3_rank_dev(const w3_smem_tab *s, uint64_t key, uint32_t pos) {
+  uint32_t r = w3_rank_lookup(key, pos & 7u, s->thr, s->cell);
+  if (r == 0xFFFFFFFFu)
+    r = w3_rank_of_hash(w3_achash_exact(w3_key_of_history(key), pos, s->table, (int)s->max_bits).hash);
+  return r;
 }
 
 __device__ __forceinline__ uint32_t w3_bswap(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
@@ -143,9 +144,10 @@ w3_encode_blocks_warp(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t
       const uint32_t bit = (w2 >> (31u - lane)) & 1u;
       const uint64_t key = ((uint64_t)__brev(hist_lo) << 32) | __brev(hist_hi);
 
-      /* ctx = (hash << 3) | alignment — ordern_entropy.rs:43-44; ctx_0 = 0 (:20) */
-      uint32_t ctx = (w3_hash_dev(st, key, t) << W3_ALIGN_BITS) | (t & 7u);
-      if (t == 0) ctx = 0;
+      /* ctx = (hash << 3) | alignment — ordern_entropy.rs:43-44; ctx_0 = 0 (:20);
+       * relabelled by rank, see W3_CTX0_RANKED in w3_core.cuh */
+      uint32_t ctx = (w3_rank_dev(st, key, t) << W3_ALIGN_BITS) | (t & 7u);
+      if (t == 0) ctx = W3_CTX0_RANKED;
       if (!active) ctx = 0x10000u | lane; /* unique: matches nobody */
 
       /* counter state each lane would see in sequential order */
@@ -284,7 +286,7 @@ w3_decode_blocks_warp(const uint8_t *__restrict__ comp, const uint64_t *__restri
   uint32_t x1 = 0, x2 = 0xFFFFFFFFu;
   uint32_t x = w3_reader_take(rd, 32); /* new_decoder — arithmetic_coder.rs:75-78 */
   uint64_t key = 0;                    /* ACHistory.bits, newest bit at bit 63 */
-  uint32_t ctx = 0, t = 0, word = 0;
+  uint32_t ctx = W3_CTX0_RANKED, t = 0, word = 0;
 
   for (uint32_t i = 0; i < n; i++) {
     uint32_t byte = 0;
@@ -303,7 +305,7 @@ w3_decode_blocks_warp(const uint8_t *__restrict__ comp, const uint64_t *__restri
       __syncwarp();
       key = (key >> 1) | ((uint64_t)bit << 63);
       t++;
-      ctx = (w3_hash_dev(st, key, t) << W3_ALIGN_BITS) | (t & 7u);
+      ctx = (w3_rank_dev(st, key, t) << W3_ALIGN_BITS) | (t & 7u);
       byte = (byte << 1) | bit;
     }
     word |= byte << (8u * (i & 3u));
@@ -362,7 +364,7 @@ __global__ void w3_k_hash_array(const uint64_t *bits, const uint32_t *pos, uint3
   w3_load_tab(st, tab);
   __syncthreads();
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    out[i] = w3_hash_dev(st, w3_key_of_history(bits[i]), pos[i]);
+    out[i] = w3_hash_of_rank(w3_rank_dev(st, w3_key_of_history(bits[i]), pos[i]));
 }
 
 /* exhaustive Counter::p check: float estimate + fix-up vs the u64 statement */

@@ -11,45 +11,69 @@
  *
  *   encode   warp 0  coder: arithmetic-coder steps only, (bit, P) pairs read
  *                    from a shared-memory ring
- *            warp 1  model: the warp-parallel predict/update of the v1 kernel
- *                    (history -> threshold-table hash -> __match_any counter
+ *            warp 1  model: the warp-parallel predict/update of the warp kernel
+ *                    (history -> threshold-table rank -> __match_any counter
  *                    resolution -> Counter::p), 32 bit positions per pass
  *
- *   decode   warp 0        decoder: decode steps only.  For bit t it picks one
- *                          of 32 prepared candidates by its last 5 decoded bits
- *            warps 1,2,3,5 speculators: warp j owns positions == j (mod 4).
- *                          For position pos its 32 lanes evaluate context and
- *                          probability for all 2^5 values of bits pos-5..pos-1
- *                          as soon as bit pos-6 is known, and apply the counter
- *                          update of position pos-8.  Two positions that share
- *                          a counter are a multiple of 8 apart, hence owned by
- *                          the same warp: program order alone keeps every
- *                          counter read behind the update it depends on.
- *            warp 4        idle (keeps the decoder alone on its scheduler)
+ *   decode   warp 0   decoder: decode steps only.  For bit t it picks one of 32
+ *                     prepared probabilities by its last 5 decoded bits.
+ *            8 warps  speculators: warp j owns positions == j (mod 8).  For
+ *                     position pos its 32 lanes evaluate context and
+ *                     probability for all 2^5 values of bits pos-5..pos-1 as
+ *                     soon as bit pos-6 is known; before that, while waiting,
+ *                     it applies the counter update of position pos-8.  Two
+ *                     positions that share a counter are a multiple of 8
+ *                     apart, hence owned by the same warp: program order alone
+ *                     keeps every counter read behind the update it needs.
+ *            (warps 4, 8, 11 idle so that the decoder has scheduler 0 alone)
  *
  * Warps of one CTA talk through volatile shared-memory words; every wait is
- * bounded (W3_SPIN_LIMIT) and trips an abort flag instead of hanging.
+ * bounded (W3_SPIN_LIMIT) and trips an abort flag instead of hanging.  Rare
+ * paths (waits, stream refill, pending-bit runs) are __noinline__ so that the
+ * steady-state loop is straight-line code: a taken branch costs ~20 cycles of
+ * instruction fetch on this chain (profiles/r01_v3_*).
  */
 #pragma once
 
 #define W3_SPIN_LIMIT (1u << 25)
 #define W3_ENC_RING 64u /* groups of 32 bits in flight between model and coder */
-#define W3_SPEC_D 5     /* speculated bits per position: 2^5 = 32 lanes */
+#define W3_SPEC_D 5u    /* speculated bits per position: 2^5 = 32 lanes */
+#define W3_SPEC_WARPS 8u
 #define W3_CAND_RING 16u
 
 #define W3_ERR_OVERFLOW 1u
 #define W3_ERR_ABORT 2u
 
-__device__ __forceinline__ uint32_t w3_lds_volatile(const volatile uint32_t *p) { return *p; }
+/* shared-memory words by 32-bit address: keeps the address in a register
+ * (no generic-pointer arithmetic per access) and fixes the issue order */
+__device__ __forceinline__ uint32_t w3_saddr(const volatile void *p) {
+  return (uint32_t)__cvta_generic_to_shared(const_cast<const void *>(p));
+}
+__device__ __forceinline__ uint32_t w3_lds(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint2 w3_lds64(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void w3_sts(uint32_t a, uint32_t v) {
+  asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void w3_sts64(uint32_t a, uint2 v) {
+  asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory");
+}
 
-/* wait until (int)(*flag - v) > 0, bounded */
-__device__ __forceinline__ bool w3_wait_gt(const volatile uint32_t *flag, uint32_t v,
-                                           volatile uint32_t *abort_flag) {
-  uint32_t spins = 0;
-  while ((int32_t)(*flag - v) <= 0) {
-    if (++spins > W3_SPIN_LIMIT || *abort_flag) { *abort_flag = 1u; return false; }
+/* wait until (int)(word at `flag_a` - v) > 0; false (and abort raised) on timeout */
+__device__ __noinline__ bool w3_wait_gt(uint32_t flag_a, uint32_t v, uint32_t abort_a) {
+  for (uint32_t spins = 0; spins < W3_SPIN_LIMIT; spins++) {
+    if ((int32_t)(w3_lds(flag_a) - v) > 0) return true;
+    if (w3_lds(abort_a)) break;
   }
-  return true;
+  w3_sts(abort_a, 1u);
+  return false;
 }
 
 /* ------------------------------------------------------------------------ */
@@ -58,11 +82,35 @@ __device__ __forceinline__ bool w3_wait_gt(const volatile uint32_t *flag, uint32
 struct w3_enc_team {
   uint32_t stats[W3_NCTX];          /* c0 | c1 << 16 */
   uint32_t ring[W3_ENC_RING][32];   /* (p << 16) | bit per coded bit */
-  volatile uint32_t prod_done;      /* groups written by the model warp */
-  volatile uint32_t cons_done;      /* groups consumed by the coder warp */
-  volatile uint32_t abort_flag;
+  uint32_t prod_done;               /* groups written by the model warp */
+  uint32_t cons_done;               /* groups consumed by the coder warp */
+  uint32_t abort_flag;
   uint32_t pad;
 };
+
+/* coder output state, passed by value through the out-of-line slow path */
+struct w3_wstate {
+  uint64_t acc;
+  uint32_t nb, words, rev, ovf;
+};
+
+/* the general ACWriter step (pending E3 run to resolve, io.rs:83-88); rare */
+__device__ __noinline__ w3_wstate w3_writer_step_slow(w3_wstate w, uint32_t pre, int s, int k,
+                                                      uint32_t *dst, uint32_t cap_words,
+                                                      uint32_t lane) {
+  w3_writer wr;
+  wr.acc = w.acc; wr.nb = w.nb; wr.words = w.words; wr.rev = w.rev;
+  uint32_t ovf = w.ovf;
+  auto store = [&](uint32_t idx, uint32_t v) {
+    if (lane == 0) {
+      if (idx < cap_words) dst[idx] = w3_bswap(v);
+      else ovf = 1;
+    }
+  };
+  w3_writer_step(wr, pre, s, k, store);
+  w.acc = wr.acc; w.nb = wr.nb; w.words = wr.words; w.rev = wr.rev; w.ovf = ovf;
+  return w;
+}
 
 __global__ void __launch_bounds__(64)
 w3_encode_blocks_team(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t block_size,
@@ -84,6 +132,9 @@ w3_encode_blocks_team(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t
   const uint64_t off = (uint64_t)blk * block_size;
   const uint32_t n = (uint32_t)(n_total - off < block_size ? n_total - off : block_size);
   const uint32_t n_words = (n + 3u) >> 2; /* groups of 32 coded bits */
+  const uint32_t ring_a = w3_saddr(&tm->ring[0][0]) + lane * 4u;
+  const uint32_t prod_a = w3_saddr(&tm->prod_done), cons_a = w3_saddr(&tm->cons_done);
+  const uint32_t abort_a = w3_saddr(&tm->abort_flag);
 
   if (warp == 1) {
     /* ---- model warp: (bit, p) for 32 positions per pass -------------------- */
@@ -100,6 +151,7 @@ w3_encode_blocks_team(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t
     };
     uint32_t w0 = 0, w1 = 0;
     uint32_t cw_next = load_chunk(0);
+    uint32_t room = W3_ENC_RING; /* groups the coder is known to have freed */
     for (uint32_t chunk = 0; chunk * 32u < n_words; chunk++) {
       const uint32_t cw = cw_next;
       cw_next = load_chunk(chunk + 1);
@@ -116,8 +168,8 @@ w3_encode_blocks_team(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t
         const uint32_t hist_lo = __funnelshift_l(w2, w1, lane);
         const uint32_t bit = (w2 >> (31u - lane)) & 1u;
         const uint64_t key = ((uint64_t)__brev(hist_lo) << 32) | __brev(hist_hi);
-        uint32_t ctx = (w3_hash_dev(st, key, t) << W3_ALIGN_BITS) | (t & 7u);
-        if (t == 0) ctx = 0;
+        uint32_t ctx = (w3_rank_dev(st, key, t) << W3_ALIGN_BITS) | (t & 7u);
+        if (t == 0) ctx = W3_CTX0_RANKED;
         if (!active) ctx = 0x10000u | lane;
 
         const uint32_t m = __match_any_sync(FULL, ctx);
@@ -146,12 +198,15 @@ w3_encode_blocks_team(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t
             stats[ctx] = (c0 + t0) | ((c1 + t1) << 16);
         }
         /* hand the group to the coder */
-        if (g >= W3_ENC_RING && !w3_wait_gt(&tm->cons_done, g - W3_ENC_RING, &tm->abort_flag)) return;
-        ((volatile uint32_t *)tm->ring[g & (W3_ENC_RING - 1u)])[lane] = active ? ((p << 16) | bit) : 0u;
+        if (g >= room) {
+          if (!w3_wait_gt(cons_a, g - W3_ENC_RING, abort_a)) return;
+          room = w3_lds(cons_a) + W3_ENC_RING;
+        }
+        w3_sts(ring_a + (g & (W3_ENC_RING - 1u)) * 128u, active ? ((p << 16) | bit) : 0u);
         __syncwarp();
         if (lane == 0) {
           __threadfence_block();
-          tm->prod_done = g + 1u;
+          w3_sts(prod_a, g + 1u);
         }
         w0 = w1;
         w1 = w2;
@@ -163,33 +218,66 @@ w3_encode_blocks_team(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t
   /* ---- coder warp: ac.encode(bit, p) in order (main.rs:107) ----------------- */
   uint32_t *dst = reinterpret_cast<uint32_t *>(scratch + (uint64_t)blk * stride);
   const uint32_t cap_words = (uint32_t)(stride >> 2);
-  uint32_t ovf = 0;
+  uint32_t x1 = 0, x2 = 0xFFFFFFFFu;
+  w3_wstate w;
+  w.acc = 0; w.nb = 0; w.words = 0; w.rev = 0; w.ovf = 0;
+  bool dead = false;
+  uint32_t ready = 0; /* groups known to be in the ring */
+  /* one coder step; everything but narrow -> renorm is off the x1/x2 chain */
+  auto step = [&](uint32_t vj) {
+    w3_ac_narrow(x1, x2, vj & 1u, vj & 0xFFFF0000u);
+    const uint32_t pre = x1;
+    int s, k;
+    w3_ac_renorm(x1, x2, s, k);
+    if (w.rev != 0u && s != 0) {
+      w = w3_writer_step_slow(w, pre, s, k, dst, cap_words, lane);
+    } else {
+      /* append the top s bits of pre (s may be 0); then k more pending bits */
+      w.acc = (w.acc << s) | __funnelshift_l(pre, 0u, (uint32_t)s);
+      w.nb += (uint32_t)s;
+      w.rev += (uint32_t)k;
+      if (w.nb >= 32u) {
+        w.nb -= 32u;
+        if (lane == 0) {
+          if (w.words < cap_words) dst[w.words] = w3_bswap((uint32_t)(w.acc >> w.nb));
+          else w.ovf = 1;
+        }
+        w.words++;
+      }
+    }
+  };
+  for (uint32_t g = 0; g < n_words; g++) {
+    if (ready <= g) {
+      if (!w3_wait_gt(prod_a, g, abort_a)) { dead = true; break; }
+      ready = w3_lds(prod_a);
+    }
+    const uint32_t v = w3_lds(ring_a + (g & (W3_ENC_RING - 1u)) * 128u);
+    const uint32_t left = n * 8u - g * 32u;
+    if (left >= 32u) {
+      /* the shuffles run two steps ahead of their use */
+      uint32_t cur = __shfl_sync(FULL, v, 0), nxt = __shfl_sync(FULL, v, 1);
+#pragma unroll 8
+      for (uint32_t j = 0; j < 32u; j++) {
+        const uint32_t vj = cur;
+        cur = nxt;
+        nxt = __shfl_sync(FULL, v, (j + 2u) & 31u);
+        step(vj);
+      }
+    } else {
+      for (uint32_t j = 0; j < left; j++) step(__shfl_sync(FULL, v, j));
+    }
+    w3_sts(cons_a, g + 1u);
+  }
+  /* ac.flush — main.rs:111 */
+  w3_writer wr;
+  wr.acc = w.acc; wr.nb = w.nb; wr.words = w.words; wr.rev = w.rev;
+  uint32_t ovf = w.ovf;
   auto store = [&](uint32_t idx, uint32_t v) {
     if (lane == 0) {
       if (idx < cap_words) dst[idx] = w3_bswap(v);
       else ovf = 1;
     }
   };
-  uint32_t x1 = 0, x2 = 0xFFFFFFFFu;
-  w3_writer wr;
-  w3_writer_init(wr);
-  bool dead = false;
-  for (uint32_t g = 0; g < n_words; g++) {
-    if (!w3_wait_gt(&tm->prod_done, g, &tm->abort_flag)) { dead = true; break; }
-    const uint32_t v = ((const volatile uint32_t *)tm->ring[g & (W3_ENC_RING - 1u)])[lane];
-    const uint32_t left = n * 8u - g * 32u;
-    const uint32_t nact = left < 32u ? left : 32u;
-#pragma unroll 4
-    for (uint32_t j = 0; j < nact; j++) {
-      const uint32_t vj = __shfl_sync(FULL, v, j);
-      w3_ac_narrow(x1, x2, vj & 1u, vj & 0xFFFF0000u);
-      const uint32_t pre = x1;
-      int s, k;
-      w3_ac_renorm(x1, x2, s, k);
-      w3_writer_step(wr, pre, s, k, store);
-    }
-    if (lane == 0) tm->cons_done = g + 1u;
-  }
   uint32_t tail, tail_bytes;
   const uint64_t len = w3_writer_flush(wr, x2, tail, tail_bytes, store);
   if (lane == 0) {
@@ -200,7 +288,7 @@ w3_encode_blocks_team(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t
     }
     lens[blk] = (uint32_t)len;
     if (ovf) atomicOr(err, W3_ERR_OVERFLOW);
-    if (dead || tm->abort_flag) atomicOr(err, W3_ERR_ABORT);
+    if (dead || w3_lds(abort_a)) atomicOr(err, W3_ERR_ABORT);
   }
 }
 
@@ -208,15 +296,57 @@ w3_encode_blocks_team(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t
 /* decode                                                                   */
 
 struct w3_dec_team {
-  uint2 stats[W3_NCTX];                  /* .x = c0 | c1 << 16, .y = Counter::p << 16 */
-  uint32_t cand[W3_CAND_RING][32];       /* (p << 16) | ctx for every guess of the last 5 bits */
-  volatile uint32_t spec_flag[W3_CAND_RING]; /* pos + 1 once cand[pos % 16] is complete */
-  volatile uint32_t pub;                 /* (bits decoded << 16) | last 16 decoded bits */
-  volatile uint32_t abort_flag;
+  uint2 stats[W3_NCTX];             /* .x = c0 | c1 << 16, .y = Counter::p << 16 */
+  uint32_t cand[W3_CAND_RING][32];  /* Counter::p << 16 for every guess of the last 5 bits */
+  uint32_t spec_flag[W3_CAND_RING]; /* pos + 1 once cand[pos % 16] is complete */
+  uint32_t pub;                     /* (bits decoded << 16) | last 16 decoded bits, newest highest */
+  uint32_t abort_flag;
   uint32_t pad[2];
 };
 
-#define W3_DEC_TEAM_THREADS 192
+#define W3_DEC_TEAM_THREADS 384
+
+/* speculator's view of the decoded prefix: K = its last 64 bits as a hash key
+ * (newest bit = bit 63, as w3_key_of_history builds it), known = how many */
+struct w3_known {
+  uint64_t K;
+  uint32_t known;
+};
+/* fold the decoder's published word into (K, known); at most 16 new bits */
+__device__ __forceinline__ void w3_known_absorb(w3_known &kn, uint32_t pv) {
+  const uint32_t delta = ((pv >> 16) - kn.known) & 0xFFFFu;
+  if (delta) {
+    kn.K = (kn.K >> delta) | ((uint64_t)((pv & 0xFFFFu) >> (16u - delta)) << (64u - delta));
+    kn.known += delta;
+  }
+}
+/* wait until at least `need` bits are known; false on abort */
+__device__ __forceinline__ bool w3_known_wait(w3_known &kn, uint32_t need, uint32_t pub_a,
+                                              uint32_t abort_a) {
+  uint32_t spins = 0;
+  for (;;) {
+    w3_known_absorb(kn, w3_lds(pub_a));
+    if (kn.known >= need) return true;
+    if (++spins > W3_SPIN_LIMIT || w3_lds(abort_a)) { w3_sts(abort_a, 1u); return false; }
+  }
+}
+
+/* decoder's stream window, passed by value through the out-of-line refill */
+struct w3_rstate {
+  uint64_t win;
+  int have;
+  uint32_t widx, cur, nxt;
+};
+__device__ __noinline__ w3_rstate w3_reader_refill(w3_rstate r, const uint32_t *ab, uint32_t sel,
+                                                   int64_t slen) {
+  w3_reader rd;
+  rd.ab = ab; rd.sel = sel; rd.slen = slen; rd.widx = r.widx; rd.cur = r.cur; rd.nxt = r.nxt;
+  rd.win = r.win; rd.have = r.have;
+  rd.win |= (uint64_t)w3_reader_word(rd) << (32 - rd.have);
+  rd.have += 32;
+  r.win = rd.win; r.have = rd.have; r.widx = rd.widx; r.cur = rd.cur; r.nxt = rd.nxt;
+  return r;
+}
 
 __global__ void __launch_bounds__(W3_DEC_TEAM_THREADS)
 w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restrict__ offsets,
@@ -236,57 +366,62 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
   __syncthreads();
 
   const uint32_t blk = blockIdx.x;
-  if (blk >= n_blocks || warp == 4) return;
+  /* warps 4, 8, 11 stay idle: scheduler 0 (warps 0, 4, 8) belongs to the decoder */
+  if (blk >= n_blocks || warp == 4 || warp == 8 || warp == 11) return;
   const uint64_t off = (uint64_t)blk * block_size;
   const uint32_t n = (uint32_t)(n_total - off < block_size ? n_total - off : block_size);
   const uint32_t nbits = n * 8u;
+  const uint32_t cand_a = w3_saddr(&tm->cand[0][0]), flag_a = w3_saddr(&tm->spec_flag[0]);
+  const uint32_t pub_a = w3_saddr(&tm->pub), abort_a = w3_saddr(&tm->abort_flag);
+  const uint32_t stats_a = w3_saddr(&tm->stats[0]);
 
   if (warp != 0) {
-    /* ---- speculator j: positions j, j+4, j+8, … ----------------------------- */
-    const uint32_t j = warp < 4 ? warp - 1u : 3u;
-    uint64_t hist = 0;   /* decoded bits, newest at bit 0 */
-    uint32_t known = 0;  /* how many of them */
-    uint32_t ctx_m4 = 0, ctx_m8 = 0; /* this lane's context guess for pos-4 / pos-8 */
-    for (uint32_t pos = j; pos < nbits; pos += 4) {
-      /* wait for bit pos-6 (bits 0 .. pos-6 known = pos-5 bits) */
-      const uint32_t need = pos > W3_SPEC_D ? pos - W3_SPEC_D : 0u;
-      uint32_t spins = 0;
-      for (;;) {
-        const uint32_t pv = tm->pub;
-        const uint32_t delta = ((pv >> 16) - known) & 0xFFFFu; /* new bits, <= 16 by construction */
-        if (known + delta >= need) {
-          hist = (hist << delta) | (uint64_t)(pv & ((1u << delta) - 1u));
-          known += delta;
-          break;
-        }
-        if (++spins > W3_SPIN_LIMIT || tm->abort_flag) { tm->abort_flag = 1u; return; }
-      }
-      /* adapt (main.rs:136 -> ordern_entropy.rs:32-34) for position pos-8, whose
-       * counter this warp owns; its context is the guess that came true */
+    /* ---- speculator j: positions j, j+8, j+16, … ---------------------------- */
+    const uint32_t j = warp - 1u - (warp > 4u) - (warp > 8u);
+    /* lane = guess of bits pos-5..pos-1, bit 0 = the newest (pos-1); in key
+     * order the newest bit is the highest */
+    const uint64_t guess_key = (uint64_t)(__brev(lane) >> (32u - W3_SPEC_D)) << (64u - W3_SPEC_D);
+    w3_known kn;
+    kn.K = 0;
+    kn.known = 0;
+    uint32_t ctx_m8 = W3_CTX0_RANKED; /* this lane's context guess for pos-8 */
+    for (uint32_t pos = j; pos < nbits; pos += W3_SPEC_WARPS) {
+      /* adapt (main.rs:136 -> ordern_entropy.rs:32-34) for position q = pos-8,
+       * whose counter this warp owns, as soon as bit q is known — i.e. while
+       * bit pos-6 is still being waited for.  The context of q is the guess
+       * that came true. */
       if (pos >= 8u) {
         const uint32_t q = pos - 8u;
-        const uint32_t hq = (uint32_t)(hist >> (known - q)) & 31u;      /* bits q-5 .. q-1 */
-        const uint32_t bq = (uint32_t)(hist >> (known - 1u - q)) & 1u;  /* bit q */
+        if (!w3_known_wait(kn, q + 1u, pub_a, abort_a)) return;
+        const uint32_t sh = 64u - kn.known + q; /* key bit of position q */
+        const uint32_t bq = (uint32_t)(kn.K >> sh) & 1u;
+        /* bits q-5..q-1 sit just below, oldest lowest: reverse into guess order */
+        const uint32_t hq = __brev((uint32_t)(kn.K >> (sh - W3_SPEC_D)) & 31u) >> (32u - W3_SPEC_D);
         const uint32_t cq = __shfl_sync(FULL, ctx_m8, hq);
-        const uint32_t nv = w3_counter_update(tm->stats[cq].x, bq);
+        const uint32_t sa = stats_a + cq * 8u;
+        const uint32_t nv = w3_counter_update(w3_lds(sa), bq);
         const uint32_t np = w3_counter_p(nv & 0xFFFFu, nv >> 16) << 16;
-        if (lane == 0) tm->stats[cq] = make_uint2(nv, np);
+        if (lane == 0) w3_sts64(sa, make_uint2(nv, np));
         __syncwarp();
       }
-      /* predict for position pos under guess `lane` of bits pos-5 .. pos-1 */
-      const uint64_t base = pos >= W3_SPEC_D ? hist >> (known - (pos - W3_SPEC_D)) : 0ull;
-      const uint64_t full = (base << W3_SPEC_D) | lane;
-      uint32_t ctx = (w3_hash_dev(st, w3_key_of_history(full), pos) << W3_ALIGN_BITS) | (pos & 7u);
-      if (pos == 0) ctx = 0;
-      const uint32_t P = tm->stats[ctx].y;
-      ((volatile uint32_t *)tm->cand[pos & (W3_CAND_RING - 1u)])[lane] = P | ctx;
+      /* predict for position pos under guess `lane` of bits pos-5 .. pos-1, once
+       * bit pos-6 is known (pos-5 bits) */
+      const uint32_t need = pos > W3_SPEC_D ? pos - W3_SPEC_D : 0u;
+      if (!w3_known_wait(kn, need, pub_a, abort_a)) return;
+      /* drop what is known beyond bit pos-6; for pos < 5 that is everything */
+      const uint32_t extra = kn.known + W3_SPEC_D - pos;
+      const uint64_t key = ((kn.K << extra) >> W3_SPEC_D) | guess_key;
+      uint32_t ctx = (w3_rank_dev(st, key, pos) << W3_ALIGN_BITS) | (pos & 7u);
+      if (pos == 0) ctx = W3_CTX0_RANKED;
+      const uint32_t P = w3_lds(stats_a + ctx * 8u + 4u);
+      const uint32_t slot = pos & (W3_CAND_RING - 1u);
+      w3_sts(cand_a + slot * 128u + lane * 4u, P);
       __syncwarp();
       if (lane == 0) {
         __threadfence_block();
-        tm->spec_flag[pos & (W3_CAND_RING - 1u)] = pos + 1u;
+        w3_sts(flag_a + slot * 4u, pos + 1u);
       }
-      ctx_m8 = ctx_m4;
-      ctx_m4 = ctx;
+      ctx_m8 = ctx;
     }
     return;
   }
@@ -297,38 +432,61 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
   w3_reader_init(rd, comp + offsets[blk], offsets[blk + 1] - offsets[blk]);
   uint32_t x1 = 0, x2 = 0xFFFFFFFFu;
   uint32_t x = w3_reader_take(rd, 32);
-  uint32_t hist = 0;
+  w3_rstate rs;
+  rs.win = rd.win; rs.have = rd.have; rs.widx = rd.widx; rs.cur = rd.cur; rs.nxt = rd.nxt;
+  uint32_t hist = 0;  /* decoded bits, newest lowest (output bytes, candidate index) */
+  uint32_t rhist = 0; /* the same, newest highest (what the speculators hash) */
   bool dead = false;
-  uint32_t flag_next = tm->spec_flag[0];
-  for (uint32_t t = 0; t < nbits; t++) {
-    /* candidate set for bit t (normally long since published) */
-    if (flag_next != t + 1u) {
-      if (!w3_wait_gt(&tm->spec_flag[t & (W3_CAND_RING - 1u)], t, &tm->abort_flag)) { dead = true; break; }
+
+  /* Candidates for bit t+1 are fetched as a pair (both values of bit t) while
+   * bit t is being decoded, so the only thing between two bits is a select. */
+  uint2 pair = make_uint2(0x80000000u, 0x80000000u);
+  uint32_t flag_next = 0; /* spec_flag of bit t+1, read one step early */
+  if (nbits) {
+    if (!w3_wait_gt(flag_a, 0u, abort_a)) dead = true;
+    pair = w3_lds64(cand_a);
+    flag_next = w3_lds(flag_a + 4u);
+  }
+  /* slot = t % 16 is a compile-time constant in the unrolled main loop */
+  auto step = [&](uint32_t t, uint32_t slot) {
+    const uint32_t P = (hist & 1u) ? pair.y : pair.x;
+    const uint32_t s1 = (slot + 1u) & (W3_CAND_RING - 1u), s2 = (slot + 2u) & (W3_CAND_RING - 1u);
+    /* bit t+1's candidates must be complete before their pair is fetched */
+    if (flag_next != t + 2u && t + 1u < nbits) {
+      if (!w3_wait_gt(flag_a + s1 * 4u, t + 1u, abort_a)) dead = true;
     }
-    const uint32_t c = ((const volatile uint32_t *)tm->cand[t & (W3_CAND_RING - 1u)])[hist & 31u];
-    flag_next = tm->spec_flag[(t + 1u) & (W3_CAND_RING - 1u)];
-    const uint32_t xmid = x1 + __umulhi(x2 - x1, c & 0xFFFF0000u);
+    const uint2 pair_n = w3_lds64(cand_a + s1 * 128u + (hist & 15u) * 8u);
+    flag_next = w3_lds(flag_a + s2 * 4u);
+    const uint32_t xmid = x1 + __umulhi(x2 - x1, P);
     const uint32_t bit = x <= xmid ? 1u : 0u; /* arithmetic_coder.rs:82 */
     if (bit) x2 = xmid; else x1 = xmid + 1u;
     hist = (hist << 1) | bit;
-    tm->pub = ((t + 1u) << 16) | (hist & 0xFFFFu);
+    rhist = __funnelshift_r(rhist, bit, 1);
+    w3_sts(pub_a, __byte_perm(rhist, t + 1u, 0x5432)); /* (t+1) << 16 | newest 16 bits */
     int s, k;
     const int nsh = w3_ac_renorm(x1, x2, s, k);
-    /* take(0) must read nothing: shift in two steps */
-    const uint32_t fresh = (uint32_t)((rd.win >> 1) >> (63 - nsh));
-    x = ((x << nsh) | fresh) ^ (k ? 0x80000000u : 0u);
-    rd.win <<= nsh;
-    rd.have -= nsh;
-    if (rd.have <= 32) {
-      rd.win |= (uint64_t)w3_reader_word(rd) << (32 - rd.have);
-      rd.have += 32;
-    }
-    if ((t & 31u) == 31u && lane == 0)
-      *reinterpret_cast<uint32_t *>(dst + (t >> 5) * 4u) = w3_bswap(hist);
+    /* x <<= nsh with stream bits shifted in; of the E3 flips only the last one
+     * survives the shifts (arithmetic_coder.rs:98-102): flip iff k > 0 */
+    const uint32_t xs = __funnelshift_l((uint32_t)(rs.win >> 32), x, (uint32_t)nsh);
+    x = xs ^ ((0u - (uint32_t)k) & 0x80000000u);
+    rs.win <<= nsh;
+    rs.have -= nsh;
+    if (rs.have <= 32) rs = w3_reader_refill(rs, rd.ab, rd.sel, rd.slen);
+    pair = pair_n;
+  };
+  uint32_t t = 0;
+  for (; t + 16u <= nbits && !dead; t += 16u) {
+#pragma unroll
+    for (uint32_t i = 0; i < 16u; i++) step(t + i, i);
+    if ((t & 16u) && lane == 0) *reinterpret_cast<uint32_t *>(dst + (t >> 5) * 4u) = w3_bswap(hist);
+  }
+  for (; t < nbits && !dead; t++) {
+    step(t, t & (W3_CAND_RING - 1u));
+    if ((t & 31u) == 31u && lane == 0) *reinterpret_cast<uint32_t *>(dst + (t >> 5) * 4u) = w3_bswap(hist);
   }
   if (lane == 0) {
     const uint32_t rem = n & 3u; /* bytes after the last whole word */
     for (uint32_t b = 0; b < rem; b++) dst[(n & ~3u) + b] = (uint8_t)(hist >> (8u * (rem - 1u - b)));
-    if (dead || tm->abort_flag) atomicOr(err, W3_ERR_ABORT);
+    if (dead || w3_lds(abort_a)) atomicOr(err, W3_ERR_ABORT);
   }
 }
