@@ -14,7 +14,9 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libw3codec.so")
 CLI = os.path.join(HERE, "w3")
 SOURCES = ["w3_kernels.cu", "w3_capi.cu"]
-DEPS = SOURCES + ["w3_core.cuh", "w3_kernels.h", os.path.join("..", "..", "include", "w3_codec.h")]
+DEPS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))) + [
+    os.path.join("..", "..", "include", "w3_codec.h")
+]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -72,6 +72,9 @@ __device__ __noinline__ bool w3_wait_gt(uint32_t flag_a, uint32_t v, uint32_t ab
     if ((int32_t)(w3_lds(flag_a) - v) > 0) return true;
     if (w3_lds(abort_a)) break;
   }
+#ifdef W3_DEBUG
+  if ((threadIdx.x & 31) == 0) printf("[w3] wait_gt timeout warp %d flag_a %u v %u cur %u\n", threadIdx.x >> 5, flag_a, v, w3_lds(flag_a));
+#endif
   w3_sts(abort_a, 1u);
   return false;
 }
@@ -215,7 +218,12 @@ w3_encode_blocks_team(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t
     return;
   }
 
-  /* ---- coder warp: ac.encode(bit, p) in order (main.rs:107) ----------------- */
+  /* ---- coder warp: ac.encode(bit, p) in order (main.rs:107) -----------------
+   * Fast path: 8 steps of straight-line code (no branch, no shuffle: the ring
+   * entry is a broadcast LDS, the word store a predicated st.global), assuming
+   * no pending E3 run has to be resolved (0.3 % of steps on text).  If one was,
+   * or the scratch region is nearly full, the 8 steps are replayed from a
+   * checkpoint by the general ACWriter code. */
   uint32_t *dst = reinterpret_cast<uint32_t *>(scratch + (uint64_t)blk * stride);
   const uint32_t cap_words = (uint32_t)(stride >> 2);
   uint32_t x1 = 0, x2 = 0xFFFFFFFFu;
@@ -223,48 +231,60 @@ w3_encode_blocks_team(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t
   w.acc = 0; w.nb = 0; w.words = 0; w.rev = 0; w.ovf = 0;
   bool dead = false;
   uint32_t ready = 0; /* groups known to be in the ring */
-  /* one coder step; everything but narrow -> renorm is off the x1/x2 chain */
-  auto step = [&](uint32_t vj) {
+  const uint32_t ring_u = w3_saddr(&tm->ring[0][0]); /* warp-uniform: entry j of the group */
+  const uint32_t is_lane0 = lane == 0 ? 1u : 0u;
+
+  auto slow_step = [&](uint32_t vj) {
     w3_ac_narrow(x1, x2, vj & 1u, vj & 0xFFFF0000u);
     const uint32_t pre = x1;
     int s, k;
     w3_ac_renorm(x1, x2, s, k);
-    if (w.rev != 0u && s != 0) {
-      w = w3_writer_step_slow(w, pre, s, k, dst, cap_words, lane);
-    } else {
-      /* append the top s bits of pre (s may be 0); then k more pending bits */
-      w.acc = (w.acc << s) | __funnelshift_l(pre, 0u, (uint32_t)s);
-      w.nb += (uint32_t)s;
-      w.rev += (uint32_t)k;
-      if (w.nb >= 32u) {
-        w.nb -= 32u;
-        if (lane == 0) {
-          if (w.words < cap_words) dst[w.words] = w3_bswap((uint32_t)(w.acc >> w.nb));
-          else w.ovf = 1;
-        }
-        w.words++;
-      }
-    }
+    w = w3_writer_step_slow(w, pre, s, k, dst, cap_words, lane);
   };
+
   for (uint32_t g = 0; g < n_words; g++) {
     if (ready <= g) {
       if (!w3_wait_gt(prod_a, g, abort_a)) { dead = true; break; }
       ready = w3_lds(prod_a);
     }
-    const uint32_t v = w3_lds(ring_a + (g & (W3_ENC_RING - 1u)) * 128u);
+    const uint32_t ga = ring_u + (g & (W3_ENC_RING - 1u)) * 128u;
     const uint32_t left = n * 8u - g * 32u;
-    if (left >= 32u) {
-      /* the shuffles run two steps ahead of their use */
-      uint32_t cur = __shfl_sync(FULL, v, 0), nxt = __shfl_sync(FULL, v, 1);
-#pragma unroll 8
-      for (uint32_t j = 0; j < 32u; j++) {
-        const uint32_t vj = cur;
-        cur = nxt;
-        nxt = __shfl_sync(FULL, v, (j + 2u) & 31u);
-        step(vj);
-      }
+    if (left < 32u || w.words + 40u > cap_words) {
+      for (uint32_t j = 0; j < (left < 32u ? left : 32u); j++) slow_step(w3_lds(ga + j * 4u));
     } else {
-      for (uint32_t j = 0; j < left; j++) step(__shfl_sync(FULL, v, j));
+#pragma unroll 1
+      for (uint32_t q = 0; q < 4u; q++) {
+        const uint32_t qa = ga + q * 32u;
+        const uint32_t cx1 = x1, cx2 = x2;
+        const w3_wstate cw = w;
+        uint32_t trouble = 0;
+        uint32_t v0 = w3_lds(qa), v1 = w3_lds(qa + 4u);
+#pragma unroll
+        for (uint32_t j = 0; j < 8u; j++) {
+          const uint32_t vj = v0;
+          v0 = v1;
+          if (j + 2u < 8u) v1 = w3_lds(qa + (j + 2u) * 4u);
+          w3_ac_narrow(x1, x2, vj & 1u, vj & 0xFFFF0000u);
+          const uint32_t pre = x1;
+          int s, k;
+          w3_ac_renorm(x1, x2, s, k);
+          trouble |= (w.rev != 0u && s != 0) ? 1u : 0u;
+          /* append the top s bits of pre (s may be 0); k more bits pending */
+          w.acc = (w.acc << s) | __funnelshift_l(pre, 0u, (uint32_t)s);
+          w.nb += (uint32_t)s;
+          w.rev += (uint32_t)k;
+          const uint32_t full = w.nb >= 32u ? 1u : 0u;
+          w.nb -= full << 5;
+          const uint32_t word = w3_bswap((uint32_t)(w.acc >> w.nb));
+          asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p st.global.u32 [%1], %2; }"
+                       ::"r"(full & is_lane0), "l"(dst + w.words), "r"(word) : "memory");
+          w.words += full;
+        }
+        if (trouble) { /* replay these 8 steps with the general writer */
+          x1 = cx1; x2 = cx2; w = cw;
+          for (uint32_t j = 0; j < 8u; j++) slow_step(w3_lds(qa + j * 4u));
+        }
+      }
     }
     w3_sts(cons_a, g + 1u);
   }
@@ -295,13 +315,17 @@ w3_encode_blocks_team(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t
 /* ------------------------------------------------------------------------ */
 /* decode                                                                   */
 
+#define W3_SRING 128u /* stream words staged in shared memory for the decoder */
+
 struct w3_dec_team {
   uint2 stats[W3_NCTX];             /* .x = c0 | c1 << 16, .y = Counter::p << 16 */
   uint32_t cand[W3_CAND_RING][32];  /* Counter::p << 16 for every guess of the last 5 bits */
+  uint2 sring[W3_SRING];            /* entry i = big-endian stream words (i, i+1) */
   uint32_t spec_flag[W3_CAND_RING]; /* pos + 1 once cand[pos % 16] is complete */
   uint32_t pub;                     /* (bits decoded << 16) | last 16 decoded bits, newest highest */
   uint32_t abort_flag;
-  uint32_t pad[2];
+  uint32_t fed;                     /* stream words staged so far (feeder -> decoder) */
+  uint32_t cons;                    /* decoder's current stream word (decoder -> feeder); ~0 = done */
 };
 
 #define W3_DEC_TEAM_THREADS 384
@@ -327,25 +351,14 @@ __device__ __forceinline__ bool w3_known_wait(w3_known &kn, uint32_t need, uint3
   for (;;) {
     w3_known_absorb(kn, w3_lds(pub_a));
     if (kn.known >= need) return true;
-    if (++spins > W3_SPIN_LIMIT || w3_lds(abort_a)) { w3_sts(abort_a, 1u); return false; }
+    if (++spins > W3_SPIN_LIMIT || w3_lds(abort_a)) {
+#ifdef W3_DEBUG
+      if ((threadIdx.x & 31) == 0) printf("[w3] known_wait timeout warp %d need %u known %u pub %08x\n", threadIdx.x >> 5, need, kn.known, w3_lds(pub_a));
+#endif
+      w3_sts(abort_a, 1u);
+      return false;
+    }
   }
-}
-
-/* decoder's stream window, passed by value through the out-of-line refill */
-struct w3_rstate {
-  uint64_t win;
-  int have;
-  uint32_t widx, cur, nxt;
-};
-__device__ __noinline__ w3_rstate w3_reader_refill(w3_rstate r, const uint32_t *ab, uint32_t sel,
-                                                   int64_t slen) {
-  w3_reader rd;
-  rd.ab = ab; rd.sel = sel; rd.slen = slen; rd.widx = r.widx; rd.cur = r.cur; rd.nxt = r.nxt;
-  rd.win = r.win; rd.have = r.have;
-  rd.win |= (uint64_t)w3_reader_word(rd) << (32 - rd.have);
-  rd.have += 32;
-  r.win = rd.win; r.have = rd.have; r.widx = rd.widx; r.cur = rd.cur; r.nxt = rd.nxt;
-  return r;
 }
 
 __global__ void __launch_bounds__(W3_DEC_TEAM_THREADS)
@@ -362,22 +375,67 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
   for (uint32_t i = threadIdx.x; i < W3_NCTX; i += blockDim.x)
     tm->stats[i] = make_uint2(0u, 0x80000000u); /* Counter::new: p = 32768 */
   if (threadIdx.x < W3_CAND_RING) tm->spec_flag[threadIdx.x] = 0;
-  if (threadIdx.x == 0) { tm->pub = 0; tm->abort_flag = 0; }
+  if (threadIdx.x == 0) { tm->pub = 0; tm->abort_flag = 0; tm->fed = 0; tm->cons = 0; }
   __syncthreads();
 
   const uint32_t blk = blockIdx.x;
-  /* warps 4, 8, 11 stay idle: scheduler 0 (warps 0, 4, 8) belongs to the decoder */
-  if (blk >= n_blocks || warp == 4 || warp == 8 || warp == 11) return;
+  /* warps 4 and 8 stay idle: scheduler 0 (warps 0, 4, 8) belongs to the decoder */
+  if (blk >= n_blocks || warp == 4 || warp == 8) return;
   const uint64_t off = (uint64_t)blk * block_size;
   const uint32_t n = (uint32_t)(n_total - off < block_size ? n_total - off : block_size);
   const uint32_t nbits = n * 8u;
   const uint32_t cand_a = w3_saddr(&tm->cand[0][0]), flag_a = w3_saddr(&tm->spec_flag[0]);
   const uint32_t pub_a = w3_saddr(&tm->pub), abort_a = w3_saddr(&tm->abort_flag);
   const uint32_t stats_a = w3_saddr(&tm->stats[0]);
+  const uint32_t sring_a = w3_saddr(&tm->sring[0]);
+  const uint32_t fed_a = w3_saddr(&tm->fed), cons_a = w3_saddr(&tm->cons);
+
+  if (warp == 11) {
+    /* ---- feeder: stages the block's stream in shared memory, as big-endian
+     * words, zero past its end (ACReader — io.rs:18-48), so that the decoder
+     * reads stream bits with one LDS and no refill branch ------------------- */
+    const uint8_t *sp = comp + offsets[blk];
+    const int64_t slen = (int64_t)(offsets[blk + 1] - offsets[blk]);
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(sp) & 3u);
+    const uint32_t *ab = reinterpret_cast<const uint32_t *>(sp - sh);
+    const uint32_t sel = ((sh + 3u) | ((sh + 2u) << 4) | ((sh + 1u) << 8) | (sh << 12));
+    uint32_t fed = 0, spins = 0;
+    for (;;) {
+      const uint32_t c = w3_lds(cons_a);
+      if (c == 0xFFFFFFFFu || w3_lds(abort_a)) break;
+      if ((int32_t)(fed - c) > (int32_t)(W3_SRING - 40u)) { /* ring full */
+        if (++spins > W3_SPIN_LIMIT) {
+#ifdef W3_DEBUG
+          if (lane == 0) printf("[w3] feeder timeout fed %u cons %u\n", fed, c);
+#endif
+          w3_sts(abort_a, 1u);
+          break;
+        }
+        continue;
+      }
+      spins = 0;
+      const uint32_t i = fed + lane;
+      const int64_t rem = slen - (int64_t)i * 4;
+      uint32_t v = 0;
+      if (rem > 0) {
+        v = __byte_perm(__ldg(ab + i), __ldg(ab + i + 1u), sel);
+        if (rem < 4) v &= 0xFFFFFFFFu << (8 * (4 - (int)rem));
+      }
+      w3_sts(sring_a + (i & (W3_SRING - 1u)) * 8u, v);
+      if (i) w3_sts(sring_a + ((i - 1u) & (W3_SRING - 1u)) * 8u + 4u, v);
+      __syncwarp();
+      fed += 32u;
+      if (lane == 0) {
+        __threadfence_block();
+        w3_sts(fed_a, fed);
+      }
+    }
+    return;
+  }
 
   if (warp != 0) {
     /* ---- speculator j: positions j, j+8, j+16, … ---------------------------- */
-    const uint32_t j = warp - 1u - (warp > 4u) - (warp > 8u);
+    const uint32_t j = warp - 1u - (warp > 4u ? 1u : 0u) - (warp > 8u ? 1u : 0u);
     /* lane = guess of bits pos-5..pos-1, bit 0 = the newest (pos-1); in key
      * order the newest bit is the highest */
     const uint64_t guess_key = (uint64_t)(__brev(lane) >> (32u - W3_SPEC_D)) << (64u - W3_SPEC_D);
@@ -426,64 +484,88 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
     return;
   }
 
-  /* ---- decoder: decode steps only (main.rs:131-140) ------------------------- */
+  /* ---- decoder: decode steps only (main.rs:131-140) -------------------------
+   * The steady state is straight-line code, 16 steps per loop trip: a branch
+   * costs this lone warp 10-40 cycles of fetch and resolve, more than the
+   * arithmetic of a step (profiles/r01_v4_*).  The only conditional left per
+   * step is "are the candidates of the next bit published", whose rare side
+   * leaves for a general step loop (`slow`) that waits, and comes back at the
+   * next multiple of 16. */
   uint8_t *dst = out + off;
-  w3_reader rd;
-  w3_reader_init(rd, comp + offsets[blk], offsets[blk + 1] - offsets[blk]);
-  uint32_t x1 = 0, x2 = 0xFFFFFFFFu;
-  uint32_t x = w3_reader_take(rd, 32);
-  w3_rstate rs;
-  rs.win = rd.win; rs.have = rd.have; rs.widx = rd.widx; rs.cur = rd.cur; rs.nxt = rd.nxt;
+  uint32_t x1 = 0, x2 = 0xFFFFFFFFu, x = 0;
+  uint32_t bp = 32;   /* stream bits consumed (x holds the first 32) */
   uint32_t hist = 0;  /* decoded bits, newest lowest (output bytes, candidate index) */
   uint32_t rhist = 0; /* the same, newest highest (what the speculators hash) */
   bool dead = false;
-
-  /* Candidates for bit t+1 are fetched as a pair (both values of bit t) while
-   * bit t is being decoded, so the only thing between two bits is a select. */
   uint2 pair = make_uint2(0x80000000u, 0x80000000u);
   uint32_t flag_next = 0; /* spec_flag of bit t+1, read one step early */
-  if (nbits) {
-    if (!w3_wait_gt(flag_a, 0u, abort_a)) dead = true;
-    pair = w3_lds64(cand_a);
-    flag_next = w3_lds(flag_a + 4u);
-  }
-  /* slot = t % 16 is a compile-time constant in the unrolled main loop */
-  auto step = [&](uint32_t t, uint32_t slot) {
+  uint32_t t = 0;
+
+  /* One decode step.  Candidates for bit t+1 are fetched as a pair (both
+   * values of bit t) while bit t is decoded, so that a select is all that
+   * separates two bits; stream bits come from the staged ring. */
+  auto step = [&](uint32_t tt, uint32_t slot) {
     const uint32_t P = (hist & 1u) ? pair.y : pair.x;
     const uint32_t s1 = (slot + 1u) & (W3_CAND_RING - 1u), s2 = (slot + 2u) & (W3_CAND_RING - 1u);
-    /* bit t+1's candidates must be complete before their pair is fetched */
-    if (flag_next != t + 2u && t + 1u < nbits) {
-      if (!w3_wait_gt(flag_a + s1 * 4u, t + 1u, abort_a)) dead = true;
-    }
     const uint2 pair_n = w3_lds64(cand_a + s1 * 128u + (hist & 15u) * 8u);
     flag_next = w3_lds(flag_a + s2 * 4u);
+    const uint2 sw = w3_lds64(sring_a + ((bp >> 5) & (W3_SRING - 1u)) * 8u);
     const uint32_t xmid = x1 + __umulhi(x2 - x1, P);
     const uint32_t bit = x <= xmid ? 1u : 0u; /* arithmetic_coder.rs:82 */
     if (bit) x2 = xmid; else x1 = xmid + 1u;
     hist = (hist << 1) | bit;
     rhist = __funnelshift_r(rhist, bit, 1);
-    w3_sts(pub_a, __byte_perm(rhist, t + 1u, 0x5432)); /* (t+1) << 16 | newest 16 bits */
+    w3_sts(pub_a, __byte_perm(rhist, tt + 1u, 0x5432)); /* (t+1) << 16 | newest 16 bits */
     int s, k;
     const int nsh = w3_ac_renorm(x1, x2, s, k);
     /* x <<= nsh with stream bits shifted in; of the E3 flips only the last one
      * survives the shifts (arithmetic_coder.rs:98-102): flip iff k > 0 */
-    const uint32_t xs = __funnelshift_l((uint32_t)(rs.win >> 32), x, (uint32_t)nsh);
-    x = xs ^ ((0u - (uint32_t)k) & 0x80000000u);
-    rs.win <<= nsh;
-    rs.have -= nsh;
-    if (rs.have <= 32) rs = w3_reader_refill(rs, rd.ab, rd.sel, rd.slen);
+    const uint32_t fresh = __funnelshift_l(sw.y, sw.x, bp & 31u);
+    x = __funnelshift_l(fresh, x, (uint32_t)nsh) ^ ((0u - (uint32_t)k) & 0x80000000u);
+    bp += (uint32_t)nsh;
     pair = pair_n;
   };
-  uint32_t t = 0;
-  for (; t + 16u <= nbits && !dead; t += 16u) {
+  /* make sure the staged stream reaches `words` beyond the current position */
+  auto need_stream = [&](uint32_t words) -> bool {
+    const uint32_t cur = bp >> 5;
+    w3_sts(cons_a, cur);
+    if ((int32_t)(w3_lds(fed_a) - (cur + words)) >= 0) return true;
+    return w3_wait_gt(fed_a, cur + words - 1u, abort_a);
+  };
+
+  if (nbits) {
+    if (!need_stream(3u) || !w3_wait_gt(flag_a, 0u, abort_a)) dead = true;
+    x = w3_lds(sring_a);
+    pair = w3_lds64(cand_a);
+    flag_next = w3_lds(flag_a + 4u);
+  }
+  while (t < nbits && !dead) {
+    if ((t & 15u) == 0u && t + 16u <= nbits && need_stream(18u)) {
+      /* fast trip: 16 straight-line steps */
+      bool bail = false;
 #pragma unroll
-    for (uint32_t i = 0; i < 16u; i++) step(t + i, i);
-    if ((t & 16u) && lane == 0) *reinterpret_cast<uint32_t *>(dst + (t >> 5) * 4u) = w3_bswap(hist);
+      for (uint32_t i = 0; i < 16u; i++) {
+        if (flag_next != t + i + 2u) { t += i; bail = true; break; }
+        step(t + i, i);
+      }
+      if (!bail) {
+        t += 16u;
+        if (!(t & 16u) && lane == 0) *reinterpret_cast<uint32_t *>(dst + (t >> 5) * 4u - 4u) = w3_bswap(hist);
+        continue;
+      }
+    }
+    /* general steps, up to the next multiple of 16 */
+    do {
+      if (flag_next != t + 2u && t + 1u < nbits) {
+        if (!w3_wait_gt(flag_a + ((t + 1u) & (W3_CAND_RING - 1u)) * 4u, t + 1u, abort_a)) { dead = true; break; }
+      }
+      if (!need_stream(3u)) { dead = true; break; }
+      step(t, t & (W3_CAND_RING - 1u));
+      t++;
+      if ((t & 31u) == 0u && lane == 0) *reinterpret_cast<uint32_t *>(dst + (t >> 5) * 4u - 4u) = w3_bswap(hist);
+    } while ((t & 15u) != 0u && t < nbits);
   }
-  for (; t < nbits && !dead; t++) {
-    step(t, t & (W3_CAND_RING - 1u));
-    if ((t & 31u) == 31u && lane == 0) *reinterpret_cast<uint32_t *>(dst + (t >> 5) * 4u) = w3_bswap(hist);
-  }
+  w3_sts(cons_a, 0xFFFFFFFFu); /* releases the feeder */
   if (lane == 0) {
     const uint32_t rem = n & 3u; /* bytes after the last whole word */
     for (uint32_t b = 0; b < rem; b++) dst[(n & ~3u) + b] = (uint8_t)(hist >> (8u * (rem - 1u - b)));
