@@ -107,6 +107,24 @@ int hs_compress_block(const w3_hashtab *tab, const uint8_t *in, size_t n, uint8_
   return len > cap ? -1 : 0;
 }
 
+/* (p << 16) | bit for every coded bit of a block: the coder's input sequence
+ * (used by tools/microbench to feed realistic statistics) */
+void hs_trace_block(const w3_hashtab *tab, const uint8_t *in, size_t n, uint32_t *entries) {
+  std::vector<uint32_t> stats(W3_NCTX, 0u);
+  uint32_t ctx = 0;
+  uint64_t hist = 0, t = 0;
+  for (size_t i = 0; i < n; i++)
+    for (int kbit = 7; kbit >= 0; kbit--) {
+      uint32_t bit = (in[i] >> kbit) & 1u;
+      uint32_t slot = stats[ctx];
+      uint32_t p = w3_counter_p(slot & 0xFFFFu, slot >> 16);
+      stats[ctx] = w3_counter_update(slot, bit);
+      hist = (hist << 1) | bit;
+      entries[t++] = (p << 16) | bit;
+      ctx = (hs_hash(tab, hist, (uint32_t)t, nullptr) << 3) | (uint32_t)(t & 7u);
+    }
+}
+
 /* scalar decode of one block stream */
 int hs_decompress_block(const w3_hashtab *tab, const uint8_t *in, size_t n_in, uint8_t *out,
                         size_t n_out) {

@@ -482,7 +482,7 @@ cudaError_t w3_launch_encode(const uint8_t *d_in, uint64_t n_total, uint32_t blo
                              int sm_count, cudaStream_t s) {
   if (!n_blocks) return cudaSuccess;
   if (w3_use_team(n_blocks, sm_count)) {
-    w3_encode_blocks_team<<<n_blocks, 64, sizeof(w3_smem_tab) + sizeof(w3_enc_team), s>>>(
+    w3_encode_blocks_team<<<n_blocks, W3_ENC_TEAM_THREADS, sizeof(w3_smem_tab) + sizeof(w3_enc_team), s>>>(
         d_in, n_total, block_size, n_blocks, d_scratch, stride, d_lens, d_overflow, d_tab);
     return cudaGetLastError();
   }

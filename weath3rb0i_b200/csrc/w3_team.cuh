@@ -82,40 +82,24 @@ __device__ __noinline__ bool w3_wait_gt(uint32_t flag_a, uint32_t v, uint32_t ab
 /* ------------------------------------------------------------------------ */
 /* encode                                                                   */
 
+#define W3_OUT_RING 16u /* groups of 32 coder steps in flight between coder and writer */
+
 struct w3_enc_team {
-  uint32_t stats[W3_NCTX];          /* c0 | c1 << 16 */
-  uint32_t ring[W3_ENC_RING][32];   /* (p << 16) | bit per coded bit */
-  uint32_t prod_done;               /* groups written by the model warp */
-  uint32_t cons_done;               /* groups consumed by the coder warp */
+  uint32_t stats[W3_NCTX];            /* c0 | c1 << 16 */
+  uint32_t ring[W3_ENC_RING][32];     /* model -> coder: (p << 16) | bit per coded bit */
+  uint2 oring[W3_OUT_RING][32];       /* coder -> writer: x1 before renorm, s | k << 8 per step */
+  uint32_t prod_done;                 /* groups written by the model warp */
+  uint32_t cons_done;                 /* groups consumed by the coder warp */
+  uint32_t out_done;                  /* groups of steps published by the coder warp */
+  uint32_t wr_done;                   /* groups consumed by the writer warp */
+  uint32_t final_x2;                  /* x2 at the end of the block, for ac.flush */
   uint32_t abort_flag;
-  uint32_t pad;
+  uint32_t pad[2];
 };
 
-/* coder output state, passed by value through the out-of-line slow path */
-struct w3_wstate {
-  uint64_t acc;
-  uint32_t nb, words, rev, ovf;
-};
+#define W3_ENC_TEAM_THREADS 96
 
-/* the general ACWriter step (pending E3 run to resolve, io.rs:83-88); rare */
-__device__ __noinline__ w3_wstate w3_writer_step_slow(w3_wstate w, uint32_t pre, int s, int k,
-                                                      uint32_t *dst, uint32_t cap_words,
-                                                      uint32_t lane) {
-  w3_writer wr;
-  wr.acc = w.acc; wr.nb = w.nb; wr.words = w.words; wr.rev = w.rev;
-  uint32_t ovf = w.ovf;
-  auto store = [&](uint32_t idx, uint32_t v) {
-    if (lane == 0) {
-      if (idx < cap_words) dst[idx] = w3_bswap(v);
-      else ovf = 1;
-    }
-  };
-  w3_writer_step(wr, pre, s, k, store);
-  w.acc = wr.acc; w.nb = wr.nb; w.words = wr.words; w.rev = wr.rev; w.ovf = ovf;
-  return w;
-}
-
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(W3_ENC_TEAM_THREADS)
 w3_encode_blocks_team(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t block_size,
                       uint32_t n_blocks, uint8_t *__restrict__ scratch, uint64_t stride,
                       uint32_t *__restrict__ lens, uint32_t *__restrict__ err,
@@ -127,7 +111,9 @@ w3_encode_blocks_team(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t
 
   w3_load_tab(st, tab);
   for (uint32_t i = threadIdx.x; i < W3_NCTX; i += blockDim.x) tm->stats[i] = 0u;
-  if (threadIdx.x == 0) { tm->prod_done = 0; tm->cons_done = 0; tm->abort_flag = 0; }
+  if (threadIdx.x == 0) {
+    tm->prod_done = 0; tm->cons_done = 0; tm->out_done = 0; tm->wr_done = 0; tm->abort_flag = 0;
+  }
   __syncthreads();
 
   const uint32_t blk = blockIdx.x;
@@ -137,6 +123,7 @@ w3_encode_blocks_team(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t
   const uint32_t n_words = (n + 3u) >> 2; /* groups of 32 coded bits */
   const uint32_t ring_a = w3_saddr(&tm->ring[0][0]) + lane * 4u;
   const uint32_t prod_a = w3_saddr(&tm->prod_done), cons_a = w3_saddr(&tm->cons_done);
+  const uint32_t out_a = w3_saddr(&tm->out_done), wr_a = w3_saddr(&tm->wr_done);
   const uint32_t abort_a = w3_saddr(&tm->abort_flag);
 
   if (warp == 1) {
@@ -218,86 +205,123 @@ w3_encode_blocks_team(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t
     return;
   }
 
-  /* ---- coder warp: ac.encode(bit, p) in order (main.rs:107) -----------------
-   * Fast path: 8 steps of straight-line code (no branch, no shuffle: the ring
-   * entry is a broadcast LDS, the word store a predicated st.global), assuming
-   * no pending E3 run has to be resolved (0.3 % of steps on text).  If one was,
-   * or the scratch region is nearly full, the 8 steps are replayed from a
-   * checkpoint by the general ACWriter code. */
-  uint32_t *dst = reinterpret_cast<uint32_t *>(scratch + (uint64_t)blk * stride);
-  const uint32_t cap_words = (uint32_t)(stride >> 2);
-  uint32_t x1 = 0, x2 = 0xFFFFFFFFu;
-  w3_wstate w;
-  w.acc = 0; w.nb = 0; w.words = 0; w.rev = 0; w.ovf = 0;
-  bool dead = false;
-  uint32_t ready = 0; /* groups known to be in the ring */
-  const uint32_t ring_u = w3_saddr(&tm->ring[0][0]); /* warp-uniform: entry j of the group */
-  const uint32_t is_lane0 = lane == 0 ? 1u : 0u;
-
-  auto slow_step = [&](uint32_t vj) {
-    w3_ac_narrow(x1, x2, vj & 1u, vj & 0xFFFF0000u);
-    const uint32_t pre = x1;
-    int s, k;
-    w3_ac_renorm(x1, x2, s, k);
-    w = w3_writer_step_slow(w, pre, s, k, dst, cap_words, lane);
-  };
-
-  for (uint32_t g = 0; g < n_words; g++) {
-    if (ready <= g) {
-      if (!w3_wait_gt(prod_a, g, abort_a)) { dead = true; break; }
-      ready = w3_lds(prod_a);
-    }
-    const uint32_t ga = ring_u + (g & (W3_ENC_RING - 1u)) * 128u;
-    const uint32_t left = n * 8u - g * 32u;
-    if (left < 32u || w.words + 40u > cap_words) {
-      for (uint32_t j = 0; j < (left < 32u ? left : 32u); j++) slow_step(w3_lds(ga + j * 4u));
-    } else {
-#pragma unroll 1
-      for (uint32_t q = 0; q < 4u; q++) {
-        const uint32_t qa = ga + q * 32u;
-        const uint32_t cx1 = x1, cx2 = x2;
-        const w3_wstate cw = w;
-        uint32_t trouble = 0;
-        uint32_t v0 = w3_lds(qa), v1 = w3_lds(qa + 4u);
+  if (warp == 0) {
+    /* ---- coder warp: the x1/x2 chain of ac.encode (main.rs:107) and nothing
+     * else.  Per step it reads one ring entry and publishes (x1 before renorm,
+     * s, k); turning those into output bits is the writer warp's job.  The
+     * steady state is 32 steps of straight-line code. */
+    uint32_t x1 = 0, x2 = 0xFFFFFFFFu;
+    uint32_t ready = 0, room = W3_OUT_RING;
+    const uint32_t ring_u = w3_saddr(&tm->ring[0][0]);
+    const uint32_t oring_u = w3_saddr(&tm->oring[0][0]);
+    for (uint32_t g = 0; g < n_words; g++) {
+      if (ready <= g) {
+        if (!w3_wait_gt(prod_a, g, abort_a)) return;
+        ready = w3_lds(prod_a);
+      }
+      if (g >= room) {
+        if (!w3_wait_gt(wr_a, g - W3_OUT_RING, abort_a)) return;
+        room = w3_lds(wr_a) + W3_OUT_RING;
+      }
+      const uint32_t ga = ring_u + (g & (W3_ENC_RING - 1u)) * 128u;
+      const uint32_t oa = oring_u + (g & (W3_OUT_RING - 1u)) * 256u;
+      const uint32_t left = n * 8u - g * 32u;
+      if (left >= 32u) {
+        uint32_t v0 = w3_lds(ga), v1 = w3_lds(ga + 4u);
 #pragma unroll
-        for (uint32_t j = 0; j < 8u; j++) {
+        for (uint32_t j = 0; j < 32u; j++) {
           const uint32_t vj = v0;
           v0 = v1;
-          if (j + 2u < 8u) v1 = w3_lds(qa + (j + 2u) * 4u);
+          if (j + 2u < 32u) v1 = w3_lds(ga + (j + 2u) * 4u);
           w3_ac_narrow(x1, x2, vj & 1u, vj & 0xFFFF0000u);
           const uint32_t pre = x1;
           int s, k;
           w3_ac_renorm(x1, x2, s, k);
-          trouble |= (w.rev != 0u && s != 0) ? 1u : 0u;
-          /* append the top s bits of pre (s may be 0); k more bits pending */
-          w.acc = (w.acc << s) | __funnelshift_l(pre, 0u, (uint32_t)s);
-          w.nb += (uint32_t)s;
-          w.rev += (uint32_t)k;
-          const uint32_t full = w.nb >= 32u ? 1u : 0u;
-          w.nb -= full << 5;
-          const uint32_t word = w3_bswap((uint32_t)(w.acc >> w.nb));
-          asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p st.global.u32 [%1], %2; }"
-                       ::"r"(full & is_lane0), "l"(dst + w.words), "r"(word) : "memory");
-          w.words += full;
+          w3_sts64(oa + j * 8u, make_uint2(pre, (uint32_t)s | ((uint32_t)k << 8)));
         }
-        if (trouble) { /* replay these 8 steps with the general writer */
-          x1 = cx1; x2 = cx2; w = cw;
-          for (uint32_t j = 0; j < 8u; j++) slow_step(w3_lds(qa + j * 4u));
+      } else {
+        for (uint32_t j = 0; j < 32u; j++) {
+          uint32_t pre = 0;
+          int s = 0, k = 0;
+          if (j < left) {
+            const uint32_t vj = w3_lds(ga + j * 4u);
+            w3_ac_narrow(x1, x2, vj & 1u, vj & 0xFFFF0000u);
+            pre = x1;
+            w3_ac_renorm(x1, x2, s, k);
+          }
+          w3_sts64(oa + j * 8u, make_uint2(pre, (uint32_t)s | ((uint32_t)k << 8)));
         }
       }
+      w3_sts(cons_a, g + 1u);
+      if (g + 1u == n_words) w3_sts(w3_saddr(&tm->final_x2), x2);
+      __threadfence_block();
+      w3_sts(out_a, g + 1u);
     }
-    w3_sts(cons_a, g + 1u);
+    if (n_words == 0) w3_sts(w3_saddr(&tm->final_x2), x2);
+    return;
   }
-  /* ac.flush — main.rs:111 */
-  w3_writer wr;
-  wr.acc = w.acc; wr.nb = w.nb; wr.words = w.words; wr.rev = w.rev;
-  uint32_t ovf = w.ovf;
+
+  /* ---- writer warp: ACWriter (io.rs:52-101) over the published steps --------
+   * Lane i holds step i of a group.  Only steps with s > 0 emit anything (about
+   * one in seven on text); the pending-bit count each of them meets is a
+   * difference of prefix sums of k, so the warp walks just those steps. */
+  uint32_t *dst = reinterpret_cast<uint32_t *>(scratch + (uint64_t)blk * stride);
+  const uint32_t cap_words = (uint32_t)(stride >> 2);
+  uint32_t ovf = 0;
+  bool dead = false;
   auto store = [&](uint32_t idx, uint32_t v) {
     if (lane == 0) {
       if (idx < cap_words) dst[idx] = w3_bswap(v);
       else ovf = 1;
     }
   };
+  w3_writer wr;
+  w3_writer_init(wr);
+  const uint32_t oring_l = w3_saddr(&tm->oring[0][0]) + lane * 8u;
+  uint32_t have = 0;
+  for (uint32_t g = 0; g < n_words; g++) {
+    if (have <= g) {
+      if (!w3_wait_gt(out_a, g, abort_a)) { dead = true; break; }
+      have = w3_lds(out_a);
+    }
+    const uint2 e = w3_lds64(oring_l + (g & (W3_OUT_RING - 1u)) * 256u);
+    __syncwarp();
+    if (lane == 0) w3_sts(wr_a, g + 1u); /* entries are in registers now */
+    const uint32_t s_l = e.y & 0xFFu, k_l = e.y >> 8;
+    /* inclusive prefix sum of k over the group */
+    uint32_t pk = k_l;
+#pragma unroll
+    for (uint32_t d = 1; d < 32u; d <<= 1) {
+      const uint32_t up = __shfl_up_sync(FULL, pk, d);
+      if (lane >= d) pk += up;
+    }
+    const uint32_t total_k = __shfl_sync(FULL, pk, 31);
+    uint32_t hm = __ballot_sync(FULL, s_l != 0u);
+    /* pending bits before the group's first emitting step come from wr.rev;
+     * `base` = exclusive prefix of k at the previous emitting step */
+    uint32_t base = 0;
+    bool first = true;
+    while (hm) {
+      const uint32_t i = (uint32_t)__ffs((int)hm) - 1u;
+      hm &= hm - 1u;
+      const uint32_t pre_i = __shfl_sync(FULL, e.x, i);
+      const uint32_t s_i = __shfl_sync(FULL, s_l, i);
+      const uint32_t pk_i = __shfl_sync(FULL, pk, i);   /* inclusive */
+      const uint32_t k_i = __shfl_sync(FULL, k_l, i);
+      const uint32_t excl = pk_i - k_i;
+      /* rev met by step i: what was pending after the previous emitting step
+       * (its own k onwards), or the carried-in count plus everything so far */
+      wr.rev = first ? wr.rev + excl : excl - base;
+      w3_writer_step(wr, pre_i, (int)s_i, 0, store); /* leaves wr.rev == 0 */
+      base = excl;
+      first = false;
+    }
+    wr.rev = first ? wr.rev + total_k : total_k - base;
+  }
+  /* ac.flush — main.rs:111; the coder stored x2 before publishing its last group
+   * (an empty block never started the coder: x2 is still new_coder's) */
+  uint32_t x2 = 0xFFFFFFFFu;
+  if (n_words) x2 = w3_lds(w3_saddr(&tm->final_x2));
   uint32_t tail, tail_bytes;
   const uint64_t len = w3_writer_flush(wr, x2, tail, tail_bytes, store);
   if (lane == 0) {
