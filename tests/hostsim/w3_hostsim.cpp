@@ -23,6 +23,7 @@ int hs_build_table(const uint16_t *table, int max_bits, w3_hashtab *tab) {
     for (uint32_t j = 0; j < 256; j++) w3_build_thr(tab, a, j);
   for (uint32_t a = 0; a < 8; a++) {
     for (uint32_t c = 0; c < W3_NCELL; c++) w3_build_cell(tab, a, c);
+    for (uint32_t c = 0; c < W3_NCELL2; c++) w3_build_cell2(tab, a, c);
     for (uint32_t r = 0; r < 256; r++) w3_build_rval(tab, a, r);
   }
   return tab->bad;
@@ -42,6 +43,18 @@ uint32_t hs_hash(const w3_hashtab *tab, uint64_t bits, uint32_t pos, int *slow) 
   if (slow) *slow = h == 0xFFFFFFFFu;
   if (h == 0xFFFFFFFFu) h = w3_achash_exact(bits, pos, tab->table, tab->max_bits).hash;
   return h;
+}
+
+/* the fixed-latency lookup of the decode speculators; -1 = needs the general path */
+int hs_rank_fixed(const w3_hashtab *tab, uint64_t bits, uint32_t pos) {
+  std::vector<uint64_t> thr(8 * 256 + W3_FIX_THR, ~(uint64_t)0);
+  memcpy(thr.data(), &tab->thr[0][0], sizeof tab->thr);
+  uint32_t r = w3_rank_lookup_fixed<false>(w3_key_of_history(bits), pos & 7u, thr.data(), &tab->cell2[0][0]);
+  return r == 0xFFFFFFFFu ? -1 : (int)r;
+}
+int hs_rank(const w3_hashtab *tab, uint64_t bits, uint32_t pos) {
+  uint32_t r = w3_rank_lookup(w3_key_of_history(bits), pos & 7u, &tab->thr[0][0], &tab->cell[0][0]);
+  return r == 0xFFFFFFFFu ? -1 : (int)r;
 }
 
 /* the relabelled context the kernels use: (rank << 3) | alignment */

@@ -131,3 +131,35 @@ def test_rank_relabelled_counters_change_nothing(libs):
             assert libs.hostsim.decompress_block(c, len(data)) == data
     finally:
         libs.hostsim.lib.hs_set_ranked(0)
+
+
+def test_fixed_latency_rank_lookup(libs):
+    """w3_rank_lookup_fixed (decode speculators) agrees with the general lookup
+    wherever it answers, and answers almost always."""
+    import ctypes as C
+
+    lib = libs.hostsim.lib
+    lib.hs_rank_fixed.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32]
+    lib.hs_rank.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32]
+    rnd = random.Random(17)
+    data = w3_corpus.generate(20000, offset=999)
+    keys, hist, t = [], 0, 0
+    for byte in data[:4000]:
+        for k in range(7, -1, -1):
+            hist = ((hist << 1) | ((byte >> k) & 1)) & ((1 << 64) - 1)
+            t += 1
+            keys.append((hist, t))
+    keys += [(rnd.getrandbits(64), rnd.randrange(64)) for _ in range(30000)]
+    thr, _ = libs.hostsim.thresholds()
+    for a in range(8):
+        for j in range(0, 255, 7):
+            keys.append((int(f"{thr[a][j]:064b}"[::-1], 2), a))
+    miss = 0
+    for bits, pos in keys:
+        f = lib.hs_rank_fixed(libs.hostsim.tab, bits, pos)
+        g = lib.hs_rank(libs.hostsim.tab, bits, pos)
+        if f < 0:
+            miss += 1
+        else:
+            assert f == g, (hex(bits), pos)
+    assert miss < len(keys) // 50

@@ -44,6 +44,11 @@
 /* first-level cell index of the threshold table: top W3_PB key bits */
 #define W3_PB 11
 #define W3_NCELL (1 << W3_PB)
+/* the decode speculators use a finer first level (fewer thresholds per cell,
+ * so that a fixed number of loads resolves a lookup): top W3_PB2 key bits */
+#define W3_PB2 13
+#define W3_NCELL2 (1 << W3_PB2)
+#define W3_FIX_THR 6 /* thresholds a fixed-latency lookup compares */
 
 W3_HD int w3_clz32(uint32_t v) {
 #if defined(__CUDA_ARCH__)
@@ -201,6 +206,7 @@ struct w3_hashtab {
   uint16_t cell[8][W3_NCELL]; /* (#thr below the cell) | (#thr inside) << 8 */
   uint8_t rval[8][256];       /* hash of regular region r = #{j : thr[j] <= K} */
   uint8_t sing[8][256];       /* 1: thr[a][j] is a singular key */
+  uint16_t cell2[8][W3_NCELL2]; /* same as cell[][] for W3_PB2 key bits */
   uint16_t table[8];          /* the StationaryModel probabilities */
   uint16_t max_bits;
   uint16_t bad;               /* set by the builder if monotonicity fails */
@@ -255,6 +261,41 @@ W3_HD uint32_t w3_rank_lookup(uint64_t key, uint32_t a, const uint64_t *thr /*[8
     eq |= key == b;
   }
   return eq ? 0xFFFFFFFFu : r;
+}
+/* Fixed-latency form for the decode speculators: W3_FIX_THR independent
+ * threshold loads, no loop.  `thr` must be readable W3_FIX_THR entries past
+ * its 8 x 256.  Returns 0xFFFFFFFF when the cell holds more thresholds than
+ * that or the key equals one of them: the caller then uses w3_rank_lookup /
+ * w3_achash_exact. */
+/* In the speculators the 32 lanes of a warp look up keys that differ only in
+ * their top (guessed) bits: with the natural layout every lane would hit the
+ * same shared-memory bank.  The swizzled layout puts the guessed bits lowest. */
+W3_HD uint32_t w3_cell2_swizzle(uint32_t c) {
+  return ((c & ((1u << (W3_PB2 - 6)) - 1u)) << 6) | (c >> (W3_PB2 - 6));
+}
+template <bool kSwizzled>
+W3_HD uint32_t w3_rank_lookup_fixed(uint64_t key, uint32_t a, const uint64_t *thr,
+                                    const uint16_t *cell2 /*[8][NCELL2]*/) {
+  uint32_t c = (uint32_t)(key >> (64 - W3_PB2));
+  uint32_t e = cell2[a * W3_NCELL2 + (kSwizzled ? w3_cell2_swizzle(c) : c)];
+  uint32_t base = e & 0xFFu, cnt = e >> 8;
+  const uint64_t *t = thr + a * 256u + base;
+  uint64_t b[W3_FIX_THR];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < W3_FIX_THR; i++) b[i] = t[i];
+  uint32_t r = base;
+  bool bad = cnt > (uint32_t)W3_FIX_THR;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < W3_FIX_THR; i++) {
+    bool in = (uint32_t)i < cnt;
+    r += (in && key >= b[i]) ? 1u : 0u;
+    bad |= in && key == b[i];
+  }
+  return bad ? 0xFFFFFFFFu : r;
 }
 W3_HD uint32_t w3_hash_of_rank(uint32_t r) { return w3_brev32(255u - r) >> 24; }
 W3_HD uint32_t w3_rank_of_hash(uint32_t h) { return 255u - (w3_brev32(h) >> 24); }
@@ -347,6 +388,17 @@ W3_HD void w3_build_cell(w3_hashtab *tab, uint32_t a, uint32_t c) {
     inside += (b >= lo && b <= hi) ? 1u : 0u;
   }
   tab->cell[a][c] = (uint16_t)(below | (inside << 8));
+}
+W3_HD void w3_build_cell2(w3_hashtab *tab, uint32_t a, uint32_t c) {
+  uint64_t lo = (uint64_t)c << (64 - W3_PB2);
+  uint64_t hi = lo | (((uint64_t)1 << (64 - W3_PB2)) - 1u);
+  uint32_t below = 0, inside = 0;
+  for (uint32_t j = 0; j < 255u; j++) {
+    uint64_t b = tab->thr[a][j];
+    below += b < lo ? 1u : 0u;
+    inside += (b >= lo && b <= hi) ? 1u : 0u;
+  }
+  tab->cell2[a][c] = (uint16_t)(below | (inside << 8));
 }
 W3_HD void w3_build_rval(w3_hashtab *tab, uint32_t a, uint32_t r) {
   /* first regular key of region r = [thr[r-1] (+1 if singular), thr[r]) */

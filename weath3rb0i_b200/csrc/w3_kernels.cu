@@ -41,6 +41,10 @@ __global__ void w3_k_build_cell_rval(w3_hashtab *tab) {
   if (i < 8u * W3_NCELL) w3_build_cell(tab, i / W3_NCELL, i % W3_NCELL);
   if (i < 8u * 256u) w3_build_rval(tab, i >> 8, i & 255u);
 }
+__global__ void w3_k_build_cell2(w3_hashtab *tab) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 8u * W3_NCELL2) w3_build_cell2(tab, i / W3_NCELL2, i % W3_NCELL2);
+}
 
 /* ------------------------------------------------------------------------ */
 /* shared-memory layout                                                     */
@@ -443,12 +447,13 @@ static inline int w3_pick_warps(uint32_t n_blocks, int sm_count) {
 }
 
 /* W3_MODE=warp|team overrides the choice; by default the team kernels run while
- * every block's CTA can be resident at once (3 CTAs of ~66 KiB smem per SM) */
-static inline bool w3_use_team(uint32_t n_blocks, int sm_count) {
+ * every block's CTA can be resident at once (encode: 3 CTAs of ~68 KiB shared
+ * memory per SM; decode: 1 CTA of ~170 KiB) */
+static inline bool w3_use_team(uint32_t n_blocks, int sm_count, uint32_t ctas_per_sm) {
   const char *m = getenv("W3_MODE");
   if (m && !strcmp(m, "warp")) return false;
   if (m && !strcmp(m, "team")) return true;
-  return n_blocks <= 3u * (uint32_t)sm_count;
+  return n_blocks <= ctas_per_sm * (uint32_t)sm_count;
 }
 
 extern "C" {
@@ -456,6 +461,7 @@ extern "C" {
 cudaError_t w3_launch_build_table(w3_hashtab *d_tab, cudaStream_t s) {
   w3_k_build_thr<<<8, 256, 0, s>>>(d_tab);
   w3_k_build_cell_rval<<<(8 * W3_NCELL + 255) / 256, 256, 0, s>>>(d_tab);
+  w3_k_build_cell2<<<(8 * W3_NCELL2 + 255) / 256, 256, 0, s>>>(d_tab);
   return cudaGetLastError();
 }
 
@@ -470,7 +476,7 @@ cudaError_t w3_kernels_init(void) {
                            (int)(sizeof(w3_smem_tab) + sizeof(w3_enc_team)));
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(w3_decode_blocks_team, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)(sizeof(w3_smem_tab) + sizeof(w3_dec_team)));
+                           (int)(sizeof(w3_dec_tab) + sizeof(w3_dec_team)));
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(w3_k_hash_array, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)sizeof(w3_smem_tab));
@@ -481,7 +487,7 @@ cudaError_t w3_launch_encode(const uint8_t *d_in, uint64_t n_total, uint32_t blo
                              uint32_t *d_lens, uint32_t *d_overflow, const w3_hashtab *d_tab,
                              int sm_count, cudaStream_t s) {
   if (!n_blocks) return cudaSuccess;
-  if (w3_use_team(n_blocks, sm_count)) {
+  if (w3_use_team(n_blocks, sm_count, 3u)) {
     w3_encode_blocks_team<<<n_blocks, W3_ENC_TEAM_THREADS, sizeof(w3_smem_tab) + sizeof(w3_enc_team), s>>>(
         d_in, n_total, block_size, n_blocks, d_scratch, stride, d_lens, d_overflow, d_tab);
     return cudaGetLastError();
@@ -515,9 +521,9 @@ cudaError_t w3_launch_decode(const uint8_t *d_comp, const uint64_t *d_offsets, u
                              uint32_t *d_err, const w3_hashtab *d_tab, int sm_count,
                              cudaStream_t s) {
   if (!n_blocks) return cudaSuccess;
-  if (w3_use_team(n_blocks, sm_count)) {
+  if (w3_use_team(n_blocks, sm_count, 1u)) {
     w3_decode_blocks_team<<<n_blocks, W3_DEC_TEAM_THREADS,
-                            sizeof(w3_smem_tab) + sizeof(w3_dec_team), s>>>(
+                            sizeof(w3_dec_tab) + sizeof(w3_dec_team), s>>>(
         d_comp, d_offsets, n_blocks, block_size, n_total, d_out, d_err, d_tab);
     return cudaGetLastError();
   }

@@ -37,7 +37,8 @@
 
 #define W3_SPIN_LIMIT (1u << 25)
 #define W3_ENC_RING 64u /* groups of 32 bits in flight between model and coder */
-#define W3_SPEC_D 5u    /* speculated bits per position: 2^5 = 32 lanes */
+#define W3_SPEC_D 5u    /* speculated bits per position: 2^D guesses, 2^(D-5) per lane */
+#define W3_GPL (1u << (W3_SPEC_D - 5u)) /* guesses per lane */
 #define W3_SPEC_WARPS 8u
 #define W3_CAND_RING 16u
 
@@ -340,19 +341,87 @@ w3_encode_blocks_team(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t
 /* decode                                                                   */
 
 #define W3_SRING 128u /* stream words staged in shared memory for the decoder */
+#define W3_NGUESS (1u << W3_SPEC_D)
+
+#define W3_THI_ROW 264u
+/* the speculators' copy of the threshold table: finer first level (W3_PB2) */
+struct w3_dec_tab {
+  uint64_t thr[8 * 256 + 8];          /* full thresholds, for the general search */
+  uint32_t thi[8 * W3_THI_ROW];       /* their high words, rows padded with ~0: fixed lookups read W3_FIX_THR ahead */
+  uint16_t cell2[8 * W3_NCELL2];
+  uint16_t table[8];
+  uint32_t max_bits;
+  uint32_t pad[3];
+};
+static_assert(sizeof(w3_dec_tab) % 16 == 0, "smem table must keep 16-byte alignment");
 
 struct w3_dec_team {
-  uint2 stats[W3_NCTX];             /* .x = c0 | c1 << 16, .y = Counter::p << 16 */
-  uint32_t cand[W3_CAND_RING][32];  /* Counter::p << 16 for every guess of the last 5 bits */
-  uint2 sring[W3_SRING];            /* entry i = big-endian stream words (i, i+1) */
-  uint32_t spec_flag[W3_CAND_RING]; /* pos + 1 once cand[pos % 16] is complete */
-  uint32_t pub;                     /* (bits decoded << 16) | last 16 decoded bits, newest highest */
+  uint2 stats[W3_NCTX + 8];                 /* .x = c0 | c1 << 16, .y = Counter::p << 16; + read padding */
+  uint32_t cand[W3_CAND_RING][W3_NGUESS];   /* (Counter::p << 16) | tag for every guess of the last 6 bits;
+                                               tag = (pos + 1) & 0xFFFF marks the entry as position pos's */
+  uint2 sring[W3_SRING];                    /* entry i = big-endian stream words (i, i+1) */
+  uint32_t spec_flag[W3_CAND_RING];         /* pos + 1 once cand[pos % 16] is complete */
+  uint32_t pub;                             /* (bits decoded << 16) | last 16 decoded bits, newest highest */
   uint32_t abort_flag;
-  uint32_t fed;                     /* stream words staged so far (feeder -> decoder) */
-  uint32_t cons;                    /* decoder's current stream word (decoder -> feeder); ~0 = done */
+  uint32_t fed;                             /* stream words staged so far (feeder -> decoder) */
+  uint32_t cons;                            /* decoder's current stream word (decoder -> feeder); ~0 = done */
 };
 
 #define W3_DEC_TEAM_THREADS 384
+
+/* counter slot of context (rank << 3) | alignment: alignment-major, so that the
+ * 32 guesses of a warp (same alignment, scattered ranks) spread over the banks */
+__device__ __forceinline__ uint32_t w3_dec_slot(uint32_t ctx) { return ((ctx & 7u) << 8) | (ctx >> 3); }
+
+/* One guess's fixed-latency lookup, written so that two of them share a basic
+ * block and interleave.  `sw` is the swizzled cell index, `khi` the key's high
+ * word.  The cell entry gives the rank range [base, base + cnt]; the high words
+ * of the next W3_FIX_THR thresholds AND the probability of every rank in the
+ * range are loaded at once (the counter slots depend only on base), so the
+ * chain is LDS -> LDS -> compare -> select.  Thresholds ascend globally, so
+ * those past the cell compare greater by themselves.
+ * bad = more than W3_FIX_THR thresholds in the cell, or a tie on the high
+ * word: the caller falls back to the general (64-bit) search. */
+struct w3_fix { uint32_t r, P, e; bool bad; };
+__device__ __forceinline__ w3_fix w3_rank_fixed_sw(uint32_t khi, uint32_t a, uint32_t sw,
+                                                   const uint32_t *thi, const uint16_t *cell2,
+                                                   uint32_t stats_a) {
+  const uint32_t e = cell2[a * W3_NCELL2 + sw];
+  const uint32_t base = e & 0xFFu;
+  const uint32_t *t = thi + a * W3_THI_ROW + base;
+  uint32_t b[W3_FIX_THR];
+#pragma unroll
+  for (int i = 0; i < W3_FIX_THR; i++) b[i] = t[i];
+  /* slot of context (rank << 3) | a is a * 256 + rank (w3_dec_slot); ranks past
+   * 255 cannot be selected, their reads stay inside the table's padding */
+  const uint32_t pa = stats_a + (a * 256u + base) * 8u + 4u;
+  uint32_t Pc[W3_FIX_THR + 1];
+#pragma unroll
+  for (int i = 0; i <= W3_FIX_THR; i++) Pc[i] = w3_lds(pa + (uint32_t)i * 8u);
+  /* thresholds ascend: the compares read 1..1 0..0, the answer is Pc[their sum].
+   * Everything below is a tree, not a chain (this warp issues in order: a
+   * serial count of six would delay the publishing store by ~50 cycles). */
+  bool gt[W3_FIX_THR];
+  bool bad = e > (((uint32_t)W3_FIX_THR << 8) | 0xFFu);
+#pragma unroll
+  for (int i = 0; i < W3_FIX_THR; i++) {
+    gt[i] = khi > b[i];
+    bad |= khi == b[i];
+  }
+  static_assert(W3_FIX_THR == 6, "the select/sum trees below are written for six thresholds");
+  const uint32_t Pa = gt[1] ? Pc[2] : (gt[0] ? Pc[1] : Pc[0]);
+  const uint32_t Pb = gt[3] ? Pc[4] : Pc[3];
+  const uint32_t Pd = gt[5] ? Pc[6] : Pc[5];
+  const uint32_t P = gt[4] ? Pd : (gt[2] ? Pb : Pa);
+  const uint32_t r = base + (((gt[0] ? 1u : 0u) + (gt[1] ? 1u : 0u) + (gt[2] ? 1u : 0u)) +
+                             ((gt[3] ? 1u : 0u) + (gt[4] ? 1u : 0u) + (gt[5] ? 1u : 0u)));
+  w3_fix f;
+  f.r = r;
+  f.P = P;
+  f.e = e;
+  f.bad = bad;
+  return f;
+}
 
 /* speculator's view of the decoded prefix: K = its last 64 bits as a hash key
  * (newest bit = bit 63, as w3_key_of_history builds it), known = how many */
@@ -368,21 +437,39 @@ __device__ __forceinline__ void w3_known_absorb(w3_known &kn, uint32_t pv) {
     kn.known += delta;
   }
 }
-/* wait until at least `need` bits are known; false on abort */
+/* wait until at least `need` bits are known; false on abort.  The spin itself
+ * is as small as it gets (the waiting warps share a scheduler with a working
+ * one); the published word is folded in once, afterwards. */
 __device__ __forceinline__ bool w3_known_wait(w3_known &kn, uint32_t need, uint32_t pub_a,
                                               uint32_t abort_a) {
-  uint32_t spins = 0;
-  for (;;) {
-    w3_known_absorb(kn, w3_lds(pub_a));
-    if (kn.known >= need) return true;
-    if (++spins > W3_SPIN_LIMIT || w3_lds(abort_a)) {
+  if (kn.known >= need) return true;
+  const uint32_t want = need & 0xFFFFu;
+  uint32_t pv = w3_lds(pub_a);
+  for (uint32_t spins = 0; (int32_t)(((pv >> 16) - want) << 16) < 0; spins++) {
+    if (spins > W3_SPIN_LIMIT || ((spins & 1023u) == 1023u && w3_lds(abort_a))) {
 #ifdef W3_DEBUG
       if ((threadIdx.x & 31) == 0) printf("[w3] known_wait timeout warp %d need %u known %u pub %08x\n", threadIdx.x >> 5, need, kn.known, w3_lds(pub_a));
 #endif
       w3_sts(abort_a, 1u);
       return false;
     }
+    pv = w3_lds(pub_a);
   }
+  w3_known_absorb(kn, pv);
+  return true;
+}
+
+/* decoder: re-fetch the candidate pair at `pa` until both entries carry `tag`
+ * (out of line: the decoder's steady state must fall through) */
+__device__ __noinline__ uint2 w3_pair_spin(uint32_t pa, uint32_t tag, uint32_t abort_a) {
+  uint2 pr = make_uint2(0u, 0u);
+  for (uint32_t spins = 0; spins < W3_SPIN_LIMIT; spins++) {
+    pr = w3_lds64(pa);
+    if ((((pr.x ^ tag) | (pr.y ^ tag)) & 0xFFFFu) == 0u) return pr;
+    if ((spins & 255u) == 255u && w3_lds(abort_a)) break;
+  }
+  w3_sts(abort_a, 1u);
+  return pr;
 }
 
 __global__ void __launch_bounds__(W3_DEC_TEAM_THREADS)
@@ -391,13 +478,29 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
                       uint8_t *__restrict__ out, uint32_t *__restrict__ err,
                       const w3_hashtab *__restrict__ tab) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  w3_smem_tab *st = reinterpret_cast<w3_smem_tab *>(smem_raw);
-  w3_dec_team *tm = reinterpret_cast<w3_dec_team *>(smem_raw + sizeof(w3_smem_tab));
+  w3_dec_tab *st = reinterpret_cast<w3_dec_tab *>(smem_raw);
+  w3_dec_team *tm = reinterpret_cast<w3_dec_team *>(smem_raw + sizeof(w3_dec_tab));
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
 
-  w3_load_tab(st, tab);
-  for (uint32_t i = threadIdx.x; i < W3_NCTX; i += blockDim.x)
+  {
+    const uint4 *gt = reinterpret_cast<const uint4 *>(&tab->thr[0][0]);
+    uint4 *dt = reinterpret_cast<uint4 *>(st->thr);
+    for (uint32_t i = threadIdx.x; i < 8u * 256u * 8u / 16u; i += blockDim.x) dt[i] = gt[i];
+    if (threadIdx.x < 8) st->thr[8 * 256 + threadIdx.x] = ~(uint64_t)0;
+    for (uint32_t i = threadIdx.x; i < 8u * W3_THI_ROW; i += blockDim.x) {
+      const uint32_t row = i / W3_THI_ROW, col = i % W3_THI_ROW;
+      st->thi[i] = col < 255u ? (uint32_t)(__ldg(&tab->thr[row][col]) >> 32) : 0xFFFFFFFFu;
+    }
+    /* cell2 goes in swizzled: see w3_cell2_swizzle (bank conflicts) */
+    const uint16_t *gc = &tab->cell2[0][0];
+    for (uint32_t i = threadIdx.x; i < 8u * W3_NCELL2; i += blockDim.x)
+      st->cell2[(i & ~(W3_NCELL2 - 1u)) | w3_cell2_swizzle(i & (W3_NCELL2 - 1u))] = __ldg(gc + i);
+    if (threadIdx.x < 8) st->table[threadIdx.x] = tab->table[threadIdx.x];
+    if (threadIdx.x == 0) st->max_bits = tab->max_bits;
+  }
+  for (uint32_t i = threadIdx.x; i < W3_NCTX + 8u; i += blockDim.x)
     tm->stats[i] = make_uint2(0u, 0x80000000u); /* Counter::new: p = 32768 */
+  for (uint32_t i = threadIdx.x; i < W3_CAND_RING * W3_NGUESS; i += blockDim.x) (&tm->cand[0][0])[i] = 0u;
   if (threadIdx.x < W3_CAND_RING) tm->spec_flag[threadIdx.x] = 0;
   if (threadIdx.x == 0) { tm->pub = 0; tm->abort_flag = 0; tm->fed = 0; tm->cons = 0; }
   __syncthreads();
@@ -460,51 +563,110 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
   if (warp != 0) {
     /* ---- speculator j: positions j, j+8, j+16, … ---------------------------- */
     const uint32_t j = warp - 1u - (warp > 4u ? 1u : 0u) - (warp > 8u ? 1u : 0u);
-    /* lane = guess of bits pos-5..pos-1, bit 0 = the newest (pos-1); in key
-     * order the newest bit is the highest */
-    const uint64_t guess_key = (uint64_t)(__brev(lane) >> (32u - W3_SPEC_D)) << (64u - W3_SPEC_D);
+    /* a guess g (W3_SPEC_D bits) of bits pos-D..pos-1 has bit 0 = the newest
+     * (pos-1); in key order the newest bit is the highest.  This lane owns the
+     * guesses lane + 32 i, i < W3_GPL. */
+    uint32_t ghi[W3_GPL]; /* the guess as the top bits of the key's high word */
+#pragma unroll
+    for (uint32_t i = 0; i < W3_GPL; i++) ghi[i] = __brev(lane + 32u * i) >> (32u - W3_SPEC_D) << (32u - W3_SPEC_D);
+    /* general search, for the rare guess the fixed-latency lookup declines */
+    auto rank_slow = [&](uint64_t key, uint32_t pos, uint32_t e) -> uint32_t {
+      uint32_t r = e & 0xFFu;
+      const uint32_t cnt = e >> 8;
+      const uint64_t *t = st->thr + (pos & 7u) * 256u + r;
+      bool eq = false;
+      for (uint32_t i = 0; i < cnt; i++) { r += key >= t[i] ? 1u : 0u; eq |= key == t[i]; }
+      if (eq) r = w3_rank_of_hash(w3_achash_exact(w3_key_of_history(key), pos, st->table, (int)st->max_bits).hash);
+      return r;
+    };
     w3_known kn;
     kn.K = 0;
     kn.known = 0;
-    uint32_t ctx_m8 = W3_CTX0_RANKED; /* this lane's context guess for pos-8 */
+    uint32_t ctx_m8[W3_GPL]; /* this lane's context guesses for pos-8 */
+#pragma unroll
+    for (uint32_t i = 0; i < W3_GPL; i++) ctx_m8[i] = W3_CTX0_RANKED;
+#ifdef W3_DEBUG
+    long long dbg_wait = 0, dbg_work = 0, dbg_n = 0, dbg_look = 0, dbg_pub = 0, dbg_fall = 0;
+#endif
     for (uint32_t pos = j; pos < nbits; pos += W3_SPEC_WARPS) {
       /* adapt (main.rs:136 -> ordern_entropy.rs:32-34) for position q = pos-8,
-       * whose counter this warp owns, as soon as bit q is known — i.e. while
-       * bit pos-6 is still being waited for.  The context of q is the guess
-       * that came true. */
+       * whose counter this warp owns.  Its context — the guess that came true —
+       * is known one bit before bit q itself: both outcomes are prepared then,
+       * and committed with a select when bit q arrives. */
       if (pos >= 8u) {
         const uint32_t q = pos - 8u;
-        if (!w3_known_wait(kn, q + 1u, pub_a, abort_a)) return;
-        const uint32_t sh = 64u - kn.known + q; /* key bit of position q */
-        const uint32_t bq = (uint32_t)(kn.K >> sh) & 1u;
-        /* bits q-5..q-1 sit just below, oldest lowest: reverse into guess order */
-        const uint32_t hq = __brev((uint32_t)(kn.K >> (sh - W3_SPEC_D)) & 31u) >> (32u - W3_SPEC_D);
-        const uint32_t cq = __shfl_sync(FULL, ctx_m8, hq);
-        const uint32_t sa = stats_a + cq * 8u;
-        const uint32_t nv = w3_counter_update(w3_lds(sa), bq);
-        const uint32_t np = w3_counter_p(nv & 0xFFFFu, nv >> 16) << 16;
-        if (lane == 0) w3_sts64(sa, make_uint2(nv, np));
+        if (!w3_known_wait(kn, q, pub_a, abort_a)) return; /* bits < q */
+        /* bits q-D..q-1 are the newest ones of K: oldest lowest, reverse into guess order */
+        const uint32_t shq = 64u - kn.known + q; /* key bit position q would take */
+        const uint32_t hq = __brev((uint32_t)(kn.K >> (shq - W3_SPEC_D)) & (W3_NGUESS - 1u)) >> (32u - W3_SPEC_D);
+        uint32_t cq = __shfl_sync(FULL, ctx_m8[0], hq & 31u);
+#pragma unroll
+        for (uint32_t i = 1; i < W3_GPL; i++) {
+          const uint32_t ci = __shfl_sync(FULL, ctx_m8[i], hq & 31u);
+          cq = (hq >> 5) == i ? ci : cq;
+        }
+        const uint32_t sa = stats_a + w3_dec_slot(cq) * 8u;
+        const uint32_t old = w3_lds(sa);
+        const uint32_t nv0 = w3_counter_update(old, 0u), nv1 = w3_counter_update(old, 1u);
+        const uint32_t np0 = w3_counter_p(nv0 & 0xFFFFu, nv0 >> 16) << 16;
+        const uint32_t np1 = w3_counter_p(nv1 & 0xFFFFu, nv1 >> 16) << 16;
+        if (!w3_known_wait(kn, q + 1u, pub_a, abort_a)) return; /* bit q */
+        const uint32_t bq = (uint32_t)(kn.K >> (64u - kn.known + q)) & 1u;
+        if (lane == 0) w3_sts64(sa, bq ? make_uint2(nv1, np1) : make_uint2(nv0, np0));
         __syncwarp();
       }
-      /* predict for position pos under guess `lane` of bits pos-5 .. pos-1, once
-       * bit pos-6 is known (pos-5 bits) */
+      /* predict for position pos under this lane's guesses, once bit pos-D-1
+       * is known (pos-D bits) */
       const uint32_t need = pos > W3_SPEC_D ? pos - W3_SPEC_D : 0u;
+#ifdef W3_DEBUG
+      const long long dbg_t0 = clock64();
+#endif
       if (!w3_known_wait(kn, need, pub_a, abort_a)) return;
-      /* drop what is known beyond bit pos-6; for pos < 5 that is everything */
+#ifdef W3_DEBUG
+      const long long dbg_t1 = clock64();
+#endif
+      /* drop what is known beyond bit pos-D-1; for pos < D that is everything */
       const uint32_t extra = kn.known + W3_SPEC_D - pos;
-      const uint64_t key = ((kn.K << extra) >> W3_SPEC_D) | guess_key;
-      uint32_t ctx = (w3_rank_dev(st, key, pos) << W3_ALIGN_BITS) | (pos & 7u);
-      if (pos == 0) ctx = W3_CTX0_RANKED;
-      const uint32_t P = w3_lds(stats_a + ctx * 8u + 4u);
-      const uint32_t slot = pos & (W3_CAND_RING - 1u);
-      w3_sts(cand_a + slot * 128u + lane * 4u, P);
-      __syncwarp();
-      if (lane == 0) {
-        __threadfence_block();
-        w3_sts(flag_a + slot * 4u, pos + 1u);
+      const uint64_t kb = (kn.K << extra) >> W3_SPEC_D;
+      const uint32_t kbhi = (uint32_t)(kb >> 32);
+      w3_fix f[W3_GPL];
+      bool any_bad = pos == 0u;
+#pragma unroll
+      for (uint32_t i = 0; i < W3_GPL; i++) {
+        const uint32_t khi = kbhi | ghi[i];
+        f[i] = w3_rank_fixed_sw(khi, pos & 7u, w3_cell2_swizzle(khi >> (32u - W3_PB2)), st->thi, st->cell2, stats_a);
+        any_bad |= f[i].bad;
       }
-      ctx_m8 = ctx;
+#ifdef W3_DEBUG
+      if (__any_sync(FULL, any_bad)) dbg_fall++;
+#endif
+      if (any_bad) { /* rare, and the only branch of the lookup */
+#pragma unroll
+        for (uint32_t i = 0; i < W3_GPL; i++) {
+          if (f[i].bad) f[i].r = rank_slow(kb | ((uint64_t)ghi[i] << 32), pos, f[i].e);
+          if (pos == 0u) f[i].r = W3_CTX0_RANKED >> W3_ALIGN_BITS;
+          f[i].P = w3_lds(stats_a + w3_dec_slot((f[i].r << W3_ALIGN_BITS) | (pos & 7u)) * 8u + 4u);
+        }
+      }
+#ifdef W3_DEBUG
+      const long long dbg_t2 = clock64() + (f[0].P & 0);
+#endif
+      /* publish: the tag in the low half makes each entry self-validating, so
+       * neither a flag nor a fence is needed */
+      const uint32_t tag = (pos + 1u) & 0xFFFFu;
+      const uint32_t slot = pos & (W3_CAND_RING - 1u);
+#pragma unroll
+      for (uint32_t i = 0; i < W3_GPL; i++) {
+        w3_sts(cand_a + slot * (W3_NGUESS * 4u) + i * 128u + lane * 4u, f[i].P | tag);
+        ctx_m8[i] = (f[i].r << W3_ALIGN_BITS) | (pos & 7u);
+      }
+#ifdef W3_DEBUG
+      dbg_wait += dbg_t1 - dbg_t0; dbg_work += clock64() - dbg_t1; dbg_n++; dbg_look += dbg_t2 - dbg_t1; dbg_pub += clock64() - dbg_t2;
+#endif
     }
+#ifdef W3_DEBUG
+    if (blk == 0 && lane == 0) printf("[w3] B warp %u: positions %lld, avg wait-for-bit %.1f, avg spec+publish %.1f cycles (lookups %.1f, slot+publish %.1f, warp-level fallbacks %lld)\n", warp, dbg_n, (double)dbg_wait / dbg_n, (double)dbg_work / dbg_n, (double)dbg_look / dbg_n, (double)dbg_pub / dbg_n, dbg_fall);
+#endif
     return;
   }
 
@@ -521,18 +683,17 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
   uint32_t hist = 0;  /* decoded bits, newest lowest (output bytes, candidate index) */
   uint32_t rhist = 0; /* the same, newest highest (what the speculators hash) */
   bool dead = false;
-  uint2 pair = make_uint2(0x80000000u, 0x80000000u);
-  uint32_t flag_next = 0; /* spec_flag of bit t+1, read one step early */
+  uint2 pair = make_uint2(0u, 0u); /* candidates of bit t for bit t-1 = 0 / 1 */
   uint32_t t = 0;
 
   /* One decode step.  Candidates for bit t+1 are fetched as a pair (both
    * values of bit t) while bit t is decoded, so that a select is all that
-   * separates two bits; stream bits come from the staged ring. */
+   * separates two bits; stream bits come from the staged ring.  The caller has
+   * checked the tags of `pair`. */
   auto step = [&](uint32_t tt, uint32_t slot) {
-    const uint32_t P = (hist & 1u) ? pair.y : pair.x;
-    const uint32_t s1 = (slot + 1u) & (W3_CAND_RING - 1u), s2 = (slot + 2u) & (W3_CAND_RING - 1u);
-    const uint2 pair_n = w3_lds64(cand_a + s1 * 128u + (hist & 15u) * 8u);
-    flag_next = w3_lds(flag_a + s2 * 4u);
+    const uint32_t P = ((hist & 1u) ? pair.y : pair.x) & 0xFFFF0000u;
+    const uint32_t s1 = (slot + 1u) & (W3_CAND_RING - 1u);
+    const uint2 pair_n = w3_lds64(cand_a + s1 * (W3_NGUESS * 4u) + (hist & (W3_NGUESS / 2u - 1u)) * 8u);
     const uint2 sw = w3_lds64(sring_a + ((bp >> 5) & (W3_SRING - 1u)) * 8u);
     const uint32_t xmid = x1 + __umulhi(x2 - x1, P);
     const uint32_t bit = x <= xmid ? 1u : 0u; /* arithmetic_coder.rs:82 */
@@ -549,6 +710,21 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
     bp += (uint32_t)nsh;
     pair = pair_n;
   };
+  /* both candidates of bit tt carry position tt's tag? */
+  auto pair_ok = [&](uint32_t tt) -> bool {
+    return (((pair.x ^ (tt + 1u)) | (pair.y ^ (tt + 1u))) & 0xFFFFu) == 0u;
+  };
+  /* (re)fetch bit tt's candidates until the speculator has published them */
+  auto pair_wait = [&](uint32_t tt) -> bool {
+    const uint32_t pa = cand_a + (tt & (W3_CAND_RING - 1u)) * (W3_NGUESS * 4u) + ((hist >> 1) & (W3_NGUESS / 2u - 1u)) * 8u;
+    for (uint32_t spins = 0; spins < W3_SPIN_LIMIT; spins++) {
+      pair = w3_lds64(pa);
+      if (pair_ok(tt)) return true;
+      if (w3_lds(abort_a)) break;
+    }
+    w3_sts(abort_a, 1u);
+    return false;
+  };
   /* make sure the staged stream reaches `words` beyond the current position */
   auto need_stream = [&](uint32_t words) -> bool {
     const uint32_t cur = bp >> 5;
@@ -558,37 +734,48 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
   };
 
   if (nbits) {
-    if (!need_stream(3u) || !w3_wait_gt(flag_a, 0u, abort_a)) dead = true;
+    if (!need_stream(3u)) dead = true;
     x = w3_lds(sring_a);
-    pair = w3_lds64(cand_a);
-    flag_next = w3_lds(flag_a + 4u);
   }
+#ifdef W3_DEBUG
+  long long dbg_a0 = clock64(), dbg_slow = 0, dbg_nslow = 0, dbg_spin = 0, dbg_nspin = 0;
+#endif
   while (t < nbits && !dead) {
     if ((t & 15u) == 0u && t + 16u <= nbits && need_stream(18u)) {
-      /* fast trip: 16 straight-line steps */
-      bool bail = false;
+      /* fast trip: 16 straight-line steps; a candidate pair that is not there
+       * yet is re-fetched on the spot (the speculators are at most a step or
+       * two behind), the general loop below is for the tail and stream waits */
 #pragma unroll
       for (uint32_t i = 0; i < 16u; i++) {
-        if (flag_next != t + i + 2u) { t += i; bail = true; break; }
+        /* a vote is warp-uniform: a plain predicated call, no reconvergence barrier */
+        if (__builtin_expect(__any_sync(FULL, !pair_ok(t + i)), 0))
+          pair = w3_pair_spin(cand_a + i * (W3_NGUESS * 4u) + ((hist >> 1) & (W3_NGUESS / 2u - 1u)) * 8u,
+                              t + i + 1u, abort_a);
         step(t + i, i);
       }
-      if (!bail) {
-        t += 16u;
-        if (!(t & 16u) && lane == 0) *reinterpret_cast<uint32_t *>(dst + (t >> 5) * 4u - 4u) = w3_bswap(hist);
-        continue;
-      }
+      t += 16u;
+      if (!(t & 16u) && lane == 0) *reinterpret_cast<uint32_t *>(dst + (t >> 5) * 4u - 4u) = w3_bswap(hist);
+      if (w3_lds(abort_a)) dead = true;
+      continue;
     }
     /* general steps, up to the next multiple of 16 */
+#ifdef W3_DEBUG
+    const long long dbg_s0 = clock64(); const uint32_t dbg_t_in = t;
+#endif
     do {
-      if (flag_next != t + 2u && t + 1u < nbits) {
-        if (!w3_wait_gt(flag_a + ((t + 1u) & (W3_CAND_RING - 1u)) * 4u, t + 1u, abort_a)) { dead = true; break; }
-      }
+      if (!pair_ok(t) && !pair_wait(t)) { dead = true; break; }
       if (!need_stream(3u)) { dead = true; break; }
       step(t, t & (W3_CAND_RING - 1u));
       t++;
       if ((t & 31u) == 0u && lane == 0) *reinterpret_cast<uint32_t *>(dst + (t >> 5) * 4u - 4u) = w3_bswap(hist);
     } while ((t & 15u) != 0u && t < nbits);
+#ifdef W3_DEBUG
+    dbg_slow += clock64() - dbg_s0; dbg_nslow += t - dbg_t_in;
+#endif
   }
+#ifdef W3_DEBUG
+  if (blk == 0 && lane == 0) printf("[w3] A: %u bits, %.1f cycles/bit overall; %lld bits in the general loop at %.1f cycles/bit; %lld pair waits, %.1f cycles each\n", nbits, (double)(clock64() - dbg_a0) / nbits, dbg_nslow, dbg_nslow ? (double)dbg_slow / dbg_nslow : 0.0, dbg_nspin, dbg_nspin ? (double)dbg_spin / dbg_nspin : 0.0);
+#endif
   w3_sts(cons_a, 0xFFFFFFFFu); /* releases the feeder */
   if (lane == 0) {
     const uint32_t rem = n & 3u; /* bytes after the last whole word */
