@@ -465,7 +465,7 @@ __device__ __noinline__ uint2 w3_pair_spin(uint32_t pa, uint32_t tag, uint32_t a
   uint2 pr = make_uint2(0u, 0u);
   for (uint32_t spins = 0; spins < W3_SPIN_LIMIT; spins++) {
     pr = w3_lds64(pa);
-    if ((((pr.x ^ tag) | (pr.y ^ tag)) & 0xFFFFu) == 0u) return pr;
+    if (((pr.x ^ tag) & 0xFFFFu) == 0u) return pr;
     if ((spins & 255u) == 255u && w3_lds(abort_a)) break;
   }
   w3_sts(abort_a, 1u);
@@ -563,12 +563,17 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
   if (warp != 0) {
     /* ---- speculator j: positions j, j+8, j+16, … ---------------------------- */
     const uint32_t j = warp - 1u - (warp > 4u ? 1u : 0u) - (warp > 8u ? 1u : 0u);
-    /* a guess g (W3_SPEC_D bits) of bits pos-D..pos-1 has bit 0 = the newest
-     * (pos-1); in key order the newest bit is the highest.  This lane owns the
-     * guesses lane + 32 i, i < W3_GPL. */
+    /* Guess index g (W3_SPEC_D bits) of bits pos-D..pos-1: bit 0 = the newest
+     * (pos-1), so the two values of the newest bit are neighbours (the decoder
+     * fetches them as one pair); the bits above it are the older ones in key
+     * order (pos-2 highest) — exactly the top bits of the decoder's history
+     * register, no reversal anywhere.  This lane owns guesses lane + 32 i. */
     uint32_t ghi[W3_GPL]; /* the guess as the top bits of the key's high word */
 #pragma unroll
-    for (uint32_t i = 0; i < W3_GPL; i++) ghi[i] = __brev(lane + 32u * i) >> (32u - W3_SPEC_D) << (32u - W3_SPEC_D);
+    for (uint32_t i = 0; i < W3_GPL; i++) {
+      const uint32_t g = lane + 32u * i;
+      ghi[i] = (((g & 1u) << (W3_SPEC_D - 1u)) | (g >> 1)) << (32u - W3_SPEC_D);
+    }
     /* general search, for the rare guess the fixed-latency lookup declines */
     auto rank_slow = [&](uint64_t key, uint32_t pos, uint32_t e) -> uint32_t {
       uint32_t r = e & 0xFFu;
@@ -596,9 +601,10 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
       if (pos >= 8u) {
         const uint32_t q = pos - 8u;
         if (!w3_known_wait(kn, q, pub_a, abort_a)) return; /* bits < q */
-        /* bits q-D..q-1 are the newest ones of K: oldest lowest, reverse into guess order */
+        /* bits q-D..q-1 are the newest ones of K, q-1 highest: rotate it down into the guess index */
         const uint32_t shq = 64u - kn.known + q; /* key bit position q would take */
-        const uint32_t hq = __brev((uint32_t)(kn.K >> (shq - W3_SPEC_D)) & (W3_NGUESS - 1u)) >> (32u - W3_SPEC_D);
+        const uint32_t vq = (uint32_t)(kn.K >> (shq - W3_SPEC_D)) & (W3_NGUESS - 1u);
+        const uint32_t hq = ((vq << 1) & (W3_NGUESS - 1u)) | (vq >> (W3_SPEC_D - 1u));
         uint32_t cq = __shfl_sync(FULL, ctx_m8[0], hq & 31u);
 #pragma unroll
         for (uint32_t i = 1; i < W3_GPL; i++) {
@@ -680,8 +686,8 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
   uint8_t *dst = out + off;
   uint32_t x1 = 0, x2 = 0xFFFFFFFFu, x = 0;
   uint32_t bp = 32;   /* stream bits consumed (x holds the first 32) */
-  uint32_t hist = 0;  /* decoded bits, newest lowest (output bytes, candidate index) */
-  uint32_t rhist = 0; /* the same, newest highest (what the speculators hash) */
+  uint32_t rhist = 0; /* decoded bits, newest highest: what the speculators hash, the
+                         candidate index (its top bits) and, bit-reversed, the output */
   bool dead = false;
   uint2 pair = make_uint2(0u, 0u); /* candidates of bit t for bit t-1 = 0 / 1 */
   uint32_t t = 0;
@@ -691,14 +697,13 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
    * separates two bits; stream bits come from the staged ring.  The caller has
    * checked the tags of `pair`. */
   auto step = [&](uint32_t tt, uint32_t slot) {
-    const uint32_t P = ((hist & 1u) ? pair.y : pair.x) & 0xFFFF0000u;
+    const uint32_t P = (((int32_t)rhist < 0) ? pair.y : pair.x) & 0xFFFF0000u;
     const uint32_t s1 = (slot + 1u) & (W3_CAND_RING - 1u);
-    const uint2 pair_n = w3_lds64(cand_a + s1 * (W3_NGUESS * 4u) + (hist & (W3_NGUESS / 2u - 1u)) * 8u);
+    const uint2 pair_n = w3_lds64(cand_a + s1 * (W3_NGUESS * 4u) + (rhist >> (33u - W3_SPEC_D)) * 8u);
     const uint2 sw = w3_lds64(sring_a + ((bp >> 5) & (W3_SRING - 1u)) * 8u);
     const uint32_t xmid = x1 + __umulhi(x2 - x1, P);
     const uint32_t bit = x <= xmid ? 1u : 0u; /* arithmetic_coder.rs:82 */
     if (bit) x2 = xmid; else x1 = xmid + 1u;
-    hist = (hist << 1) | bit;
     rhist = __funnelshift_r(rhist, bit, 1);
     w3_sts(pub_a, __byte_perm(rhist, tt + 1u, 0x5432)); /* (t+1) << 16 | newest 16 bits */
     int s, k;
@@ -710,13 +715,13 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
     bp += (uint32_t)nsh;
     pair = pair_n;
   };
-  /* both candidates of bit tt carry position tt's tag? */
-  auto pair_ok = [&](uint32_t tt) -> bool {
-    return (((pair.x ^ (tt + 1u)) | (pair.y ^ (tt + 1u))) & 0xFFFFu) == 0u;
-  };
+  /* do the candidates of bit tt carry position tt's tag?  Both entries of a
+   * pair are stored by neighbouring lanes of one STS (one 8-byte word, one
+   * wavefront), so they turn valid together: checking one is enough. */
+  auto pair_ok = [&](uint32_t tt) -> bool { return ((pair.x ^ (tt + 1u)) & 0xFFFFu) == 0u; };
   /* (re)fetch bit tt's candidates until the speculator has published them */
   auto pair_wait = [&](uint32_t tt) -> bool {
-    const uint32_t pa = cand_a + (tt & (W3_CAND_RING - 1u)) * (W3_NGUESS * 4u) + ((hist >> 1) & (W3_NGUESS / 2u - 1u)) * 8u;
+    const uint32_t pa = cand_a + (tt & (W3_CAND_RING - 1u)) * (W3_NGUESS * 4u) + ((rhist << 1) >> (33u - W3_SPEC_D)) * 8u;
     for (uint32_t spins = 0; spins < W3_SPIN_LIMIT; spins++) {
       pair = w3_lds64(pa);
       if (pair_ok(tt)) return true;
@@ -741,20 +746,24 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
   long long dbg_a0 = clock64(), dbg_slow = 0, dbg_nslow = 0, dbg_spin = 0, dbg_nspin = 0;
 #endif
   while (t < nbits && !dead) {
-    if ((t & 15u) == 0u && t + 16u <= nbits && need_stream(18u)) {
-      /* fast trip: 16 straight-line steps; a candidate pair that is not there
-       * yet is re-fetched on the spot (the speculators are at most a step or
-       * two behind), the general loop below is for the tail and stream waits */
+    /* 4 fast trips (64 bits, at most 62 stream words) per stream-ring check */
+    if ((t & 63u) == 0u && t + 64u <= nbits && need_stream(66u)) {
+#pragma unroll 1
+      for (uint32_t trip = 0; trip < 4u; trip++) {
+        /* fast trip: 16 straight-line steps; a candidate pair that is not there
+         * yet is re-fetched by an out-of-line spin (the speculators are at most
+         * a step or two behind) */
 #pragma unroll
-      for (uint32_t i = 0; i < 16u; i++) {
-        /* a vote is warp-uniform: a plain predicated call, no reconvergence barrier */
-        if (__builtin_expect(__any_sync(FULL, !pair_ok(t + i)), 0))
-          pair = w3_pair_spin(cand_a + i * (W3_NGUESS * 4u) + ((hist >> 1) & (W3_NGUESS / 2u - 1u)) * 8u,
-                              t + i + 1u, abort_a);
-        step(t + i, i);
+        for (uint32_t i = 0; i < 16u; i++) {
+          /* a vote is warp-uniform: a plain predicated call, no reconvergence barrier */
+          if (__builtin_expect(__any_sync(FULL, !pair_ok(t + i)), 0))
+            pair = w3_pair_spin(cand_a + i * (W3_NGUESS * 4u) + ((rhist << 1) >> (33u - W3_SPEC_D)) * 8u,
+                                t + i + 1u, abort_a);
+          step(t + i, i);
+        }
+        t += 16u;
+        if (!(t & 16u) && lane == 0) *reinterpret_cast<uint32_t *>(dst + (t >> 5) * 4u - 4u) = w3_bswap(__brev(rhist));
       }
-      t += 16u;
-      if (!(t & 16u) && lane == 0) *reinterpret_cast<uint32_t *>(dst + (t >> 5) * 4u - 4u) = w3_bswap(hist);
       if (w3_lds(abort_a)) dead = true;
       continue;
     }
@@ -767,7 +776,7 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
       if (!need_stream(3u)) { dead = true; break; }
       step(t, t & (W3_CAND_RING - 1u));
       t++;
-      if ((t & 31u) == 0u && lane == 0) *reinterpret_cast<uint32_t *>(dst + (t >> 5) * 4u - 4u) = w3_bswap(hist);
+      if ((t & 31u) == 0u && lane == 0) *reinterpret_cast<uint32_t *>(dst + (t >> 5) * 4u - 4u) = w3_bswap(__brev(rhist));
     } while ((t & 15u) != 0u && t < nbits);
 #ifdef W3_DEBUG
     dbg_slow += clock64() - dbg_s0; dbg_nslow += t - dbg_t_in;
@@ -779,6 +788,7 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
   w3_sts(cons_a, 0xFFFFFFFFu); /* releases the feeder */
   if (lane == 0) {
     const uint32_t rem = n & 3u; /* bytes after the last whole word */
+    const uint32_t hist = __brev(rhist); /* newest bit lowest */
     for (uint32_t b = 0; b < rem; b++) dst[(n & ~3u) + b] = (uint8_t)(hist >> (8u * (rem - 1u - b)));
     if (dead || w3_lds(abort_a)) atomicOr(err, W3_ERR_ABORT);
   }
