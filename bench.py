@@ -33,6 +33,21 @@ MIB = 1 << 20
 METRIC = "round-trip (compress+decompress) MB/s, 64 MiB synthetic text per GPU, 1 MiB blocks"
 
 
+def ncu_traffic(kernel: str, n: int):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full`
+    capture (profiles/r01_ncu_metrics.json, taken on the 64 MiB bench workload);
+    None for any other workload size."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_metrics.json")
+    if n != 64 * MIB or not os.path.exists(p):
+        return None
+    with open(p) as f:
+        m = json.load(f).get("decode" if "decode" in kernel else "encode", {})
+    try:
+        return int((float(m["dram__bytes_read.sum"]) + float(m["dram__bytes_write.sum"])) * 1e6)
+    except (KeyError, ValueError):
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -292,7 +307,11 @@ def run_b200(args):
                                         "decode": round(dec_ms * 1e-3 * sm_mhz * 1e6 / (block * 8), 1),
                                         "warps": warps},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 3), "peak": peak,
-                         "unit": "GB/s", "frac": round(achieved / peak, 6), "traffic": None,
+                         "unit": "GB/s", "frac": round(achieved / peak, 6),
+                         "traffic": ncu_traffic(dom, n) if block == MIB else None,
+                         "traffic_source": "profiles/r01_ncu_metrics.json (ncu --set full, same workload), bytes per launch",
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "compulsory_hbm_bytes_per_launch": n + comp_bytes,
                          "peak_source": peak_src,
                          "algorithmic": "8 context lookups (one 32-B sector each) per input byte, SURVEY.md §8(d); "
                                         "the counters live in shared memory, so this path is latency-bound, not HBM-bound"},
