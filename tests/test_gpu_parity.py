@@ -225,3 +225,57 @@ def test_result_independent_of_block_grouping(ctx):
     _, _, all_streams = split_container(ctx.compress(data, 4096))
     _, _, part = split_container(ctx.compress(data[4096 * 13 : 4096 * 29], 4096))
     assert all_streams[13:29] == part
+
+
+def test_join_of_gpu_parts_equals_whole(ctx):
+    """Host-side container join (weath3rb0i_b200/sharding.py) over GPU-coded parts."""
+    from weath3rb0i_b200 import sharding
+
+    data = w3_corpus.generate(4096 * 21 + 100)
+    whole = ctx.compress(data, 4096)
+    parts = []
+    for r in range(3):
+        lo, hi = sharding.byte_range(len(data), 4096, 3, r)
+        parts.append(ctx.compress(data[lo:hi], 4096))
+    assert sharding.join_containers(parts) == whole
+
+
+def test_two_devices_in_one_context_give_the_same_container(ctx):
+    """Blocks sharded over 2 GPUs by the library (one host thread per device)."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    data = w3_corpus.generate(65536 * 7 + 333)
+    c2 = capi.Context([0, 1])
+    try:
+        blob = c2.compress(data, 65536)
+        assert blob == ctx.compress(data, 65536)
+        assert c2.decompress(blob) == data
+    finally:
+        c2.close()
+
+
+def test_256mib_round_trip_and_sampled_blocks(ctx, libs, kernel_mode):
+    """Larger than one wave of CTAs (256 blocks on 148 SMs): lossless round trip
+    of the whole container, byte identity with the oracle on a deterministic
+    sample of blocks, and a container checksum that must not depend on the
+    kernel family that produced it."""
+    import ctypes as C
+
+    if kernel_mode == "warp":
+        pytest.skip("run once, with the launcher's own choice of kernels")
+    n, block = 256 << 20, 1 << 20
+    buf = C.create_string_buffer(n)
+    w3_corpus.generate_into(C.addressof(buf), n)
+    data = buf.raw
+    import os
+    os.environ.pop("W3_MODE", None)  # auto: team encode, warp decode at this block count
+    blob = ctx.compress(data, block)
+    _, _, streams = split_container(blob)
+    assert len(streams) == 256
+    for i in (0, 97, 148, 255):
+        assert streams[i] == libs.oracle.compress_block(data[i * block : (i + 1) * block]), i
+    assert ctx.decompress(blob) == data
+    os.environ["W3_MODE"] = "warp"
+    assert hashlib.sha256(ctx.compress(data, block)).digest() == hashlib.sha256(blob).digest()
