@@ -267,17 +267,58 @@ __device__ __forceinline__ uint32_t w3_reader_take(w3_reader &r, int c) { /* c i
   return v;
 }
 
+/* per-warp adaptive state of the dense decode kernel: probabilities cached
+ * next to the counts so that predict is one load (Counter::p is recomputed by
+ * the update, off the decode chain) */
+struct w3_dense_dec {
+  uint32_t probs[W3_NCTX];  /* Counter::p << 16 */
+  uint32_t counts[W3_NCTX]; /* c0 | c1 << 16 */
+};
+#define W3_DENSE_THI_ROW 264u
+
+/* fixed-latency rank lookup on the W3_PB table: the next six thresholds' high
+ * words are loaded at once and compared as a tree; declines (0xFFFFFFFF) when
+ * the cell holds more or the high word ties, and the general search runs */
+__device__ __forceinline__ uint32_t w3_rank_fixed_nat(uint32_t khi, uint32_t a, const w3_smem_tab *st,
+                                                      const uint32_t *thi) {
+  const uint32_t e = st->cell[a * W3_NCELL + (khi >> (32 - W3_PB))];
+  const uint32_t base = e & 0xFFu;
+  const uint32_t *t = thi + a * W3_DENSE_THI_ROW + base;
+  uint32_t b[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) b[i] = t[i];
+  bool bad = e > ((6u << 8) | 0xFFu);
+  uint32_t g[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    g[i] = khi > b[i] ? 1u : 0u;
+    bad |= khi == b[i];
+  }
+  const uint32_t r = base + ((g[0] + g[1] + g[2]) + (g[3] + g[4] + g[5]));
+  return bad ? 0xFFFFFFFFu : r;
+}
+
+/* decode, many-block regime: one warp per block, W3_MAX_WARPS blocks per CTA
+ * sharing one table copy.  Lanes 0 and 1 evaluate the context and probability
+ * of the NEXT bit for both values of the bit being decoded, in the same
+ * instruction stream as the decode step itself, so the table lookup overlaps
+ * the coder arithmetic instead of following it; a shuffle picks the survivor. */
 __global__ void __launch_bounds__(W3_MAX_WARPS * 32)
 w3_decode_blocks_warp(const uint8_t *__restrict__ comp, const uint64_t *__restrict__ offsets,
                  uint32_t n_blocks, uint32_t block_size, uint64_t n_total,
                  uint8_t *__restrict__ out, const w3_hashtab *__restrict__ tab) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   w3_smem_tab *st = reinterpret_cast<w3_smem_tab *>(smem_raw);
+  uint32_t *thi = reinterpret_cast<uint32_t *>(smem_raw + sizeof(w3_smem_tab));
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-  uint32_t *stats = reinterpret_cast<uint32_t *>(smem_raw + sizeof(w3_smem_tab)) + warp * W3_NCTX;
+  w3_dense_dec *ds = reinterpret_cast<w3_dense_dec *>(smem_raw + sizeof(w3_smem_tab) + 8u * W3_DENSE_THI_ROW * 4u) + warp;
 
   w3_load_tab(st, tab);
-  for (uint32_t i = lane; i < W3_NCTX; i += 32) stats[i] = 0u;
+  for (uint32_t i = threadIdx.x; i < 8u * W3_DENSE_THI_ROW; i += blockDim.x) {
+    const uint32_t row = i / W3_DENSE_THI_ROW, col = i % W3_DENSE_THI_ROW;
+    thi[i] = col < 255u ? (uint32_t)(__ldg(&tab->thr[row][col]) >> 32) : 0xFFFFFFFFu;
+  }
+  for (uint32_t i = lane; i < W3_NCTX; i += 32) { ds->probs[i] = 0x80000000u; ds->counts[i] = 0u; }
   __syncthreads();
 
   const uint32_t blk = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -291,26 +332,35 @@ w3_decode_blocks_warp(const uint8_t *__restrict__ comp, const uint64_t *__restri
   uint32_t x1 = 0, x2 = 0xFFFFFFFFu;
   uint32_t x = w3_reader_take(rd, 32); /* new_decoder — arithmetic_coder.rs:75-78 */
   uint64_t key = 0;                    /* ACHistory.bits, newest bit at bit 63 */
-  uint32_t ctx = W3_CTX0_RANKED, t = 0, word = 0;
+  uint32_t ctx = W3_CTX0_RANKED, P = 0x80000000u, t = 0, word = 0;
+  const uint32_t guess = lane & 1u;
 
   for (uint32_t i = 0; i < n; i++) {
     uint32_t byte = 0;
-#pragma unroll
+#pragma unroll 2
     for (int kb = 0; kb < 8; kb++) {
-      const uint32_t slot = stats[ctx];
-      const uint32_t P = w3_counter_p(slot & 0xFFFFu, slot >> 16) << 16; /* main.rs:134 */
+      /* this lane's guess of the bit being decoded -> context and P of the next one */
+      const uint64_t gkey = (key >> 1) | ((uint64_t)guess << 63);
+      uint32_t gr = w3_rank_fixed_nat((uint32_t)(gkey >> 32), (t + 1u) & 7u, st, thi);
+      if (gr == 0xFFFFFFFFu) gr = w3_rank_dev(st, gkey, t + 1u);
+      const uint32_t gctx = (gr << W3_ALIGN_BITS) | ((t + 1u) & 7u);
+      const uint32_t gP = ds->probs[gctx];
+      /* decode bit t (main.rs:134-135) */
       const uint32_t xmid = x1 + __umulhi(x2 - x1, P);
-      const uint32_t bit = x <= xmid ? 1u : 0u;                          /* :82 */
+      const uint32_t bit = x <= xmid ? 1u : 0u;
       if (bit) x2 = xmid; else x1 = xmid + 1u;
       int s, k;
       const int nsh = w3_ac_renorm(x1, x2, s, k);
-      if (nsh) x = ((x << nsh) | w3_reader_take(rd, nsh)) ^ (k ? 0x80000000u : 0u);
-      __syncwarp();
-      if (lane == 0) stats[ctx] = w3_counter_update(slot, bit);          /* main.rs:136 */
-      __syncwarp();
+      if (nsh) x = ((x << nsh) | w3_reader_take(rd, nsh)) ^ ((0u - (uint32_t)k) & 0x80000000u);
+      /* adapt counter of bit t (main.rs:136); every lane writes the same words */
+      const uint32_t nv = w3_counter_update(ds->counts[ctx], bit);
+      ds->counts[ctx] = nv;
+      ds->probs[ctx] = w3_counter_p(nv & 0xFFFFu, nv >> 16) << 16;
+      /* the guess that came true */
+      ctx = __shfl_sync(FULL, gctx, bit);
+      P = __shfl_sync(FULL, gP, bit);
       key = (key >> 1) | ((uint64_t)bit << 63);
       t++;
-      ctx = (w3_rank_dev(st, key, t) << W3_ALIGN_BITS) | (t & 7u);
       byte = (byte << 1) | bit;
     }
     word |= byte << (8u * (i & 3u));
@@ -437,6 +487,9 @@ __global__ void w3_k_ac_decode_probs(const uint8_t *in, uint32_t n_in, const uin
 static inline size_t w3_smem_bytes(int warps) {
   return sizeof(w3_smem_tab) + (size_t)warps * W3_NCTX * sizeof(uint32_t);
 }
+static inline size_t w3_dense_dec_smem_bytes(int warps) {
+  return sizeof(w3_smem_tab) + 8u * W3_DENSE_THI_ROW * 4u + (size_t)warps * sizeof(w3_dense_dec);
+}
 
 /* warps per CTA: spread blocks over all 148 SMs first, then stack warps */
 static inline int w3_pick_warps(uint32_t n_blocks, int sm_count) {
@@ -470,7 +523,8 @@ cudaError_t w3_kernels_init(void) {
   size_t mx = w3_smem_bytes(W3_MAX_WARPS);
   e = cudaFuncSetAttribute(w3_encode_blocks_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(w3_decode_blocks_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx);
+  e = cudaFuncSetAttribute(w3_decode_blocks_warp, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)w3_dense_dec_smem_bytes(W3_MAX_WARPS));
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(w3_encode_blocks_team, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)(sizeof(w3_smem_tab) + sizeof(w3_enc_team)));
@@ -529,7 +583,7 @@ cudaError_t w3_launch_decode(const uint8_t *d_comp, const uint64_t *d_offsets, u
   }
   int warps = w3_pick_warps(n_blocks, sm_count);
   uint32_t grid = (n_blocks + (uint32_t)warps - 1) / (uint32_t)warps;
-  w3_decode_blocks_warp<<<grid, warps * 32, w3_smem_bytes(warps), s>>>(
+  w3_decode_blocks_warp<<<grid, warps * 32, w3_dense_dec_smem_bytes(warps), s>>>(
       d_comp, d_offsets, n_blocks, block_size, n_total, d_out, d_tab);
   return cudaGetLastError();
 }

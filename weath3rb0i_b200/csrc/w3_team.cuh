@@ -41,6 +41,9 @@
 #define W3_GPL (1u << (W3_SPEC_D - 5u)) /* guesses per lane */
 #define W3_SPEC_WARPS 8u
 #define W3_CAND_RING 16u
+#ifndef W3_SPEC_NAP_NS
+#define W3_SPEC_NAP_NS 0 /* tried 100 ns: nanosleep is too coarse, decode 173 -> 182 cycles/bit */
+#endif
 
 #define W3_ERR_OVERFLOW 1u
 #define W3_ERR_ABORT 2u
@@ -356,7 +359,8 @@ struct w3_dec_tab {
 static_assert(sizeof(w3_dec_tab) % 16 == 0, "smem table must keep 16-byte alignment");
 
 struct w3_dec_team {
-  uint2 stats[W3_NCTX + 8];                 /* .x = c0 | c1 << 16, .y = Counter::p << 16; + read padding */
+  uint32_t probs[W3_NCTX + 8];              /* Counter::p << 16 per slot; + read padding (fixed lookups read ahead) */
+  uint32_t counts[W3_NCTX];                 /* c0 | c1 << 16 per slot; slot = alignment * 256 + rank (w3_dec_slot) */
   uint32_t cand[W3_CAND_RING][W3_NGUESS];   /* (Counter::p << 16) | tag for every guess of the last 6 bits;
                                                tag = (pos + 1) & 0xFFFF marks the entry as position pos's */
   uint2 sring[W3_SRING];                    /* entry i = big-endian stream words (i, i+1) */
@@ -385,7 +389,7 @@ __device__ __forceinline__ uint32_t w3_dec_slot(uint32_t ctx) { return ((ctx & 7
 struct w3_fix { uint32_t r, P, e; bool bad; };
 __device__ __forceinline__ w3_fix w3_rank_fixed_sw(uint32_t khi, uint32_t a, uint32_t sw,
                                                    const uint32_t *thi, const uint16_t *cell2,
-                                                   uint32_t stats_a) {
+                                                   uint32_t probs_a) {
   const uint32_t e = cell2[a * W3_NCELL2 + sw];
   const uint32_t base = e & 0xFFu;
   const uint32_t *t = thi + a * W3_THI_ROW + base;
@@ -394,10 +398,10 @@ __device__ __forceinline__ w3_fix w3_rank_fixed_sw(uint32_t khi, uint32_t a, uin
   for (int i = 0; i < W3_FIX_THR; i++) b[i] = t[i];
   /* slot of context (rank << 3) | a is a * 256 + rank (w3_dec_slot); ranks past
    * 255 cannot be selected, their reads stay inside the table's padding */
-  const uint32_t pa = stats_a + (a * 256u + base) * 8u + 4u;
+  const uint32_t pa = probs_a + (a * 256u + base) * 4u;
   uint32_t Pc[W3_FIX_THR + 1];
 #pragma unroll
-  for (int i = 0; i <= W3_FIX_THR; i++) Pc[i] = w3_lds(pa + (uint32_t)i * 8u);
+  for (int i = 0; i <= W3_FIX_THR; i++) Pc[i] = w3_lds(pa + (uint32_t)i * 4u);
   /* thresholds ascend: the compares read 1..1 0..0, the answer is Pc[their sum].
    * Everything below is a tree, not a chain (this warp issues in order: a
    * serial count of six would delay the publishing store by ~50 cycles). */
@@ -498,8 +502,10 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
     if (threadIdx.x < 8) st->table[threadIdx.x] = tab->table[threadIdx.x];
     if (threadIdx.x == 0) st->max_bits = tab->max_bits;
   }
-  for (uint32_t i = threadIdx.x; i < W3_NCTX + 8u; i += blockDim.x)
-    tm->stats[i] = make_uint2(0u, 0x80000000u); /* Counter::new: p = 32768 */
+  for (uint32_t i = threadIdx.x; i < W3_NCTX + 8u; i += blockDim.x) {
+    tm->probs[i] = 0x80000000u; /* Counter::new: p = 32768 */
+    if (i < W3_NCTX) tm->counts[i] = 0u;
+  }
   for (uint32_t i = threadIdx.x; i < W3_CAND_RING * W3_NGUESS; i += blockDim.x) (&tm->cand[0][0])[i] = 0u;
   if (threadIdx.x < W3_CAND_RING) tm->spec_flag[threadIdx.x] = 0;
   if (threadIdx.x == 0) { tm->pub = 0; tm->abort_flag = 0; tm->fed = 0; tm->cons = 0; }
@@ -513,7 +519,7 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
   const uint32_t nbits = n * 8u;
   const uint32_t cand_a = w3_saddr(&tm->cand[0][0]), flag_a = w3_saddr(&tm->spec_flag[0]);
   const uint32_t pub_a = w3_saddr(&tm->pub), abort_a = w3_saddr(&tm->abort_flag);
-  const uint32_t stats_a = w3_saddr(&tm->stats[0]);
+  const uint32_t probs_a = w3_saddr(&tm->probs[0]), counts_a = w3_saddr(&tm->counts[0]);
   const uint32_t sring_a = w3_saddr(&tm->sring[0]);
   const uint32_t fed_a = w3_saddr(&tm->fed), cons_a = w3_saddr(&tm->cons);
 
@@ -611,14 +617,17 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
           const uint32_t ci = __shfl_sync(FULL, ctx_m8[i], hq & 31u);
           cq = (hq >> 5) == i ? ci : cq;
         }
-        const uint32_t sa = stats_a + w3_dec_slot(cq) * 8u;
-        const uint32_t old = w3_lds(sa);
+        const uint32_t sq = w3_dec_slot(cq) * 4u;
+        const uint32_t old = w3_lds(counts_a + sq);
         const uint32_t nv0 = w3_counter_update(old, 0u), nv1 = w3_counter_update(old, 1u);
         const uint32_t np0 = w3_counter_p(nv0 & 0xFFFFu, nv0 >> 16) << 16;
         const uint32_t np1 = w3_counter_p(nv1 & 0xFFFFu, nv1 >> 16) << 16;
         if (!w3_known_wait(kn, q + 1u, pub_a, abort_a)) return; /* bit q */
         const uint32_t bq = (uint32_t)(kn.K >> (64u - kn.known + q)) & 1u;
-        if (lane == 0) w3_sts64(sa, bq ? make_uint2(nv1, np1) : make_uint2(nv0, np0));
+        if (lane == 0) {
+          w3_sts(counts_a + sq, bq ? nv1 : nv0);
+          w3_sts(probs_a + sq, bq ? np1 : np0);
+        }
         __syncwarp();
       }
       /* predict for position pos under this lane's guesses, once bit pos-D-1
@@ -640,7 +649,7 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
 #pragma unroll
       for (uint32_t i = 0; i < W3_GPL; i++) {
         const uint32_t khi = kbhi | ghi[i];
-        f[i] = w3_rank_fixed_sw(khi, pos & 7u, w3_cell2_swizzle(khi >> (32u - W3_PB2)), st->thi, st->cell2, stats_a);
+        f[i] = w3_rank_fixed_sw(khi, pos & 7u, w3_cell2_swizzle(khi >> (32u - W3_PB2)), st->thi, st->cell2, probs_a);
         any_bad |= f[i].bad;
       }
 #ifdef W3_DEBUG
@@ -651,7 +660,7 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
         for (uint32_t i = 0; i < W3_GPL; i++) {
           if (f[i].bad) f[i].r = rank_slow(kb | ((uint64_t)ghi[i] << 32), pos, f[i].e);
           if (pos == 0u) f[i].r = W3_CTX0_RANKED >> W3_ALIGN_BITS;
-          f[i].P = w3_lds(stats_a + w3_dec_slot((f[i].r << W3_ALIGN_BITS) | (pos & 7u)) * 8u + 4u);
+          f[i].P = w3_lds(probs_a + w3_dec_slot((f[i].r << W3_ALIGN_BITS) | (pos & 7u)) * 4u);
         }
       }
 #ifdef W3_DEBUG
@@ -666,6 +675,11 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
         w3_sts(cand_a + slot * (W3_NGUESS * 4u) + i * 128u + lane * 4u, f[i].P | tag);
         ctx_m8[i] = (f[i].r << W3_ALIGN_BITS) | (pos & 7u);
       }
+      /* nothing to do until bit pos-1 is known, about four decode steps away:
+       * stay off the shared-memory pipe the decoder depends on */
+#if W3_SPEC_NAP_NS > 0
+      __nanosleep(W3_SPEC_NAP_NS);
+#endif
 #ifdef W3_DEBUG
       dbg_wait += dbg_t1 - dbg_t0; dbg_work += clock64() - dbg_t1; dbg_n++; dbg_look += dbg_t2 - dbg_t1; dbg_pub += clock64() - dbg_t2;
 #endif
