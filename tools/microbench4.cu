@@ -18,10 +18,10 @@ __global__ void __launch_bounds__(384) k_spec(const w3_hashtab *tab, long long *
     for (uint32_t i = threadIdx.x; i < 8u * W3_NCELL2; i += blockDim.x)
       st->cell2[(i & ~(W3_NCELL2 - 1u)) | w3_cell2_swizzle(i & (W3_NCELL2 - 1u))] = __ldg(gc + i);
   }
-  for (uint32_t i = threadIdx.x; i < W3_NCTX; i += blockDim.x) tm->stats[i] = make_uint2(i, 0x80000000u ^ (i << 16));
+  for (uint32_t i = threadIdx.x; i < W3_NCTX + 8u; i += blockDim.x) tm->probs[i] = 0x80000000u ^ (i << 16);
   if (threadIdx.x == 0) { tm->pub = 0; tm->abort_flag = 0; }
   __syncthreads();
-  const uint32_t pub_a = w3_saddr(&tm->pub), stats_a = w3_saddr(&tm->stats[0]), cand_a = w3_saddr(&tm->cand[0][0]), flag_a = w3_saddr(&tm->spec_flag[0]);
+  const uint32_t pub_a = w3_saddr(&tm->pub), probs_a = w3_saddr(&tm->probs[0]), cand_a = w3_saddr(&tm->cand[0][0]);
   if (warp != 0) {
     if ((int)warp > spinners) return;
     // spin-poll like a waiting speculator until warp 0 is done
@@ -30,15 +30,15 @@ __global__ void __launch_bounds__(384) k_spec(const w3_hashtab *tab, long long *
     if (lane == 0) sink[warp] = n;
     return;
   }
-  const uint64_t gk0 = (uint64_t)(__brev(lane) >> (32u - W3_SPEC_D)) << (64u - W3_SPEC_D);
-  const uint64_t gk1 = gk0 | ((uint64_t)1 << (64u - W3_SPEC_D));
+  const uint64_t gk0 = (uint64_t)(__brev(lane) >> 26) << 58;
+  const uint64_t gk1 = gk0 | ((uint64_t)1 << 58);
   uint64_t K = 0x6f6c6c6568206f77ull;  // some text-like history
   uint32_t acc = 0;
   const int N = 20000;
   long long t0 = clock64();
   for (int it = 0; it < N; it++) {
     const uint32_t pos = (uint32_t)it;
-    const uint64_t kb = K >> W3_SPEC_D;
+    const uint64_t kb = K >> 6;
     uint32_t r0, r1;
     if (V == 0) {  // fixed lookups only
       r0 = w3_rank_lookup_fixed<true>(kb | gk0, pos & 7u, st->thr, st->cell2);
@@ -47,13 +47,13 @@ __global__ void __launch_bounds__(384) k_spec(const w3_hashtab *tab, long long *
       r0 = w3_rank_lookup_fixed<true>(kb | gk0, pos & 7u, st->thr, st->cell2);
       r1 = w3_rank_lookup_fixed<true>(kb | gk1, pos & 7u, st->thr, st->cell2);
       const uint32_t ctx0 = ((r0 & 255u) << 3) | (pos & 7u), ctx1 = ((r1 & 255u) << 3) | (pos & 7u);
-      const uint32_t P0 = w3_lds(stats_a + w3_dec_slot(ctx0) * 8u + 4u);
-      const uint32_t P1 = w3_lds(stats_a + w3_dec_slot(ctx1) * 8u + 4u);
+      const uint32_t P0 = w3_lds(probs_a + w3_dec_slot(ctx0) * 4u);
+      const uint32_t P1 = w3_lds(probs_a + w3_dec_slot(ctx1) * 4u);
       const uint32_t slot = pos & (W3_CAND_RING - 1u);
-      w3_sts(cand_a + slot * (W3_NGUESS * 4u) + lane * 4u, P0);
-      w3_sts(cand_a + slot * (W3_NGUESS * 4u) + 128u + lane * 4u, P1);
+      w3_sts(cand_a + slot * 128u + lane * 4u, P0);
+      w3_sts(cand_a + slot * 128u + lane * 4u, P1);
       __syncwarp();
-      if (lane == 0) { if (V == 1) __threadfence_block(); w3_sts(flag_a + slot * 4u, pos + 1u); }
+      if (lane == 0) { if (V == 1) __threadfence_block(); w3_sts(pub_a + 4u, pos + 1u); }
     }
     acc += r0 + r1;
     // next history depends on the result (serialises iterations like the real wait does)

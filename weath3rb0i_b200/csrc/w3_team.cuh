@@ -364,7 +364,6 @@ struct w3_dec_team {
   uint32_t cand[W3_CAND_RING][W3_NGUESS];   /* (Counter::p << 16) | tag for every guess of the last 6 bits;
                                                tag = (pos + 1) & 0xFFFF marks the entry as position pos's */
   uint2 sring[W3_SRING];                    /* entry i = big-endian stream words (i, i+1) */
-  uint32_t spec_flag[W3_CAND_RING];         /* pos + 1 once cand[pos % 16] is complete */
   uint32_t pub;                             /* (bits decoded << 16) | last 16 decoded bits, newest highest */
   uint32_t abort_flag;
   uint32_t fed;                             /* stream words staged so far (feeder -> decoder) */
@@ -507,7 +506,6 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
     if (i < W3_NCTX) tm->counts[i] = 0u;
   }
   for (uint32_t i = threadIdx.x; i < W3_CAND_RING * W3_NGUESS; i += blockDim.x) (&tm->cand[0][0])[i] = 0u;
-  if (threadIdx.x < W3_CAND_RING) tm->spec_flag[threadIdx.x] = 0;
   if (threadIdx.x == 0) { tm->pub = 0; tm->abort_flag = 0; tm->fed = 0; tm->cons = 0; }
   __syncthreads();
 
@@ -517,7 +515,7 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
   const uint64_t off = (uint64_t)blk * block_size;
   const uint32_t n = (uint32_t)(n_total - off < block_size ? n_total - off : block_size);
   const uint32_t nbits = n * 8u;
-  const uint32_t cand_a = w3_saddr(&tm->cand[0][0]), flag_a = w3_saddr(&tm->spec_flag[0]);
+  const uint32_t cand_a = w3_saddr(&tm->cand[0][0]);
   const uint32_t pub_a = w3_saddr(&tm->pub), abort_a = w3_saddr(&tm->abort_flag);
   const uint32_t probs_a = w3_saddr(&tm->probs[0]), counts_a = w3_saddr(&tm->counts[0]);
   const uint32_t sring_a = w3_saddr(&tm->sring[0]);
