@@ -116,6 +116,17 @@ def cpu_oracle_round_trip(n_blocks: int, block: int, threads: int, data_ptr: int
     return t1 - t0, t2 - t1, sum(lens)
 
 
+def workload_config(args) -> dict:
+    """The `config` object, identical for both arms."""
+    block = args.block_size
+    n_blocks = (args.mib * MIB + block - 1) // block
+    return {
+        "workload": f"{args.mib} MiB synthetic text per GPU (seed 0x77333069), {block >> 10} KiB blocks, "
+                    f"{n_blocks} blocks per GPU; step = compress + decompress of every block",
+        "block_size": block, "blocks_per_gpu": n_blocks,
+    }
+
+
 def host_threads() -> int:
     try:
         return len(os.sched_getaffinity(0))
@@ -152,15 +163,14 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round((tc + td) / args.steps * 1e3, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": f"{args.mib} MiB synthetic text per GPU, {block >> 10} KiB blocks (bounded sample: {sample})",
-                   "block_size": block},
+        "config": dict(workload_config(args), sample=sample),
         "compress_mbs": round(nbytes / 1e6 / tc, 3), "decompress_mbs": round(nbytes / 1e6 / td, 3),
         "cpu_baseline": {"value": round(value, 3), "unit": "MB/s", "cores": threads, "kind": "port",
                          "sample": sample},
         "e2e": {"value": round(value, 3), "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -294,10 +304,8 @@ def run_b200(args):
             "steps": K, "warmup": args.warmup, "ms_per_step": round(total_ms / K, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
             "data": "synthetic",
-            "config": {"workload": f"{args.mib} MiB synthetic text per GPU (seed 0x77333069), {block >> 10} KiB blocks, "
-                                   f"{n_blocks} blocks per GPU; step = encode + pack + decode",
-                       "block_size": block, "blocks_per_gpu": n_blocks,
-                       "l2": "working set per step (in + scratch + out > 190 MiB) exceeds the 126 MB L2; no explicit flush"},
+            "config": dict(workload_config(args),
+                           l2="working set per step (in + scratch + out > 190 MiB) exceeds the 126 MB L2; no explicit flush"),
             "compress_mbs": round(job_bytes / 1e6 / ((t_enc + t_pack) / K / 1e3), 3),
             "decompress_mbs": round(job_bytes / 1e6 / (dec_ms / 1e3), 3),
             "bits_per_byte": round(8.0 * comp_bytes / n, 4),
@@ -330,10 +338,29 @@ def run_b200(args):
                 "value": round(nb_cpu * block / 1e6 / (c + d), 3), "unit": "MB/s", "cores": threads, "kind": "port",
                 "compress_mbs": round(nb_cpu * block / 1e6 / c, 3), "decompress_mbs": round(nb_cpu * block / 1e6 / d, 3),
                 "sample": f"first {nb_cpu} x {block >> 10} KiB blocks of the same text, one block per core, round trip once"}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything but the final JSON line goes to stderr: libraries (NCCL's
+    version banner, for one) write to fd 1 and the driver parses stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
 def main():
@@ -346,6 +373,7 @@ def main():
     ap.add_argument("--block-size", type=int, default=MIB)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)

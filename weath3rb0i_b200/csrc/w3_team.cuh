@@ -464,10 +464,19 @@ __device__ __forceinline__ bool w3_known_wait(w3_known &kn, uint32_t need, uint3
 
 /* decoder: re-fetch the candidate pair at `pa` until both entries carry `tag`
  * (out of line: the decoder's steady state must fall through) */
+#ifdef W3_DEBUG
+__device__ unsigned long long w3_dbg_wait_cycles, w3_dbg_wait_n;
+#endif
 __device__ __noinline__ uint2 w3_pair_spin(uint32_t pa, uint32_t tag, uint32_t abort_a) {
   uint2 pr = make_uint2(0u, 0u);
+#ifdef W3_DEBUG
+  const long long dbg_t0 = clock64();
+#endif
   for (uint32_t spins = 0; spins < W3_SPIN_LIMIT; spins++) {
     pr = w3_lds64(pa);
+#ifdef W3_DEBUG
+    if (((pr.x ^ tag) & 0xFFFFu) == 0u && (threadIdx.x & 31) == 0) { atomicAdd(&w3_dbg_wait_cycles, (unsigned long long)(clock64() - dbg_t0)); atomicAdd(&w3_dbg_wait_n, 1ull); }
+#endif
     if (((pr.x ^ tag) & 0xFFFFu) == 0u) return pr;
     if ((spins & 255u) == 255u && w3_lds(abort_a)) break;
   }
@@ -755,7 +764,7 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
     x = w3_lds(sring_a);
   }
 #ifdef W3_DEBUG
-  long long dbg_a0 = clock64(), dbg_slow = 0, dbg_nslow = 0, dbg_spin = 0, dbg_nspin = 0;
+  long long dbg_a0 = clock64(), dbg_slow = 0, dbg_nslow = 0;
 #endif
   while (t < nbits && !dead) {
     /* 4 fast trips (64 bits, at most 62 stream words) per stream-ring check */
@@ -795,7 +804,7 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
 #endif
   }
 #ifdef W3_DEBUG
-  if (blk == 0 && lane == 0) printf("[w3] A: %u bits, %.1f cycles/bit overall; %lld bits in the general loop at %.1f cycles/bit; %lld pair waits, %.1f cycles each\n", nbits, (double)(clock64() - dbg_a0) / nbits, dbg_nslow, dbg_nslow ? (double)dbg_slow / dbg_nslow : 0.0, dbg_nspin, dbg_nspin ? (double)dbg_spin / dbg_nspin : 0.0);
+  if (blk == 0 && lane == 0) printf("[w3] A: %u bits, %.1f cycles/bit overall; %lld bits in the general loop at %.1f cycles/bit; all blocks so far: %llu pair waits, %.1f cycles each\n", nbits, (double)(clock64() - dbg_a0) / nbits, dbg_nslow, dbg_nslow ? (double)dbg_slow / dbg_nslow : 0.0, w3_dbg_wait_n, w3_dbg_wait_n ? (double)w3_dbg_wait_cycles / w3_dbg_wait_n : 0.0);
 #endif
   w3_sts(cons_a, 0xFFFFFFFFu); /* releases the feeder */
   if (lane == 0) {
