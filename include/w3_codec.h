@@ -50,6 +50,24 @@ int w3_ctx_create(const int *devices, int n_devices, w3_ctx **out);
 void w3_ctx_destroy(w3_ctx *ctx);
 int w3_ctx_device_count(const w3_ctx *ctx);
 
+/* ---- the StationaryModel of the entropy hash -------------------------------
+ * init_model() fixes StationaryModel::for_book1 (src/main.rs:151) and that is
+ * what a fresh context uses.  The reference also has from_table (src/models/
+ * ac_hash/stationary.rs:36-38, e.g. for_enwik7 :44-46) and new(buf) (:14-34),
+ * the latter used by its sweep binaries (src/bin/entropy-hashing-ac/main.rs:19).
+ * A context on any other model than for_book1 writes container version 2,
+ * which carries the 8 probabilities; the reference's own file format cannot
+ * (W3_F_LEGACY then fails with W3_E_ARG).  w3_decompress switches the context
+ * to the model of the container it is given. */
+
+/* StationaryModel::from_table: rebuilds the threshold tables on every device. */
+int w3_ctx_set_model(w3_ctx *ctx, const uint16_t table[8]);
+int w3_ctx_get_model(const w3_ctx *ctx, uint16_t table[8]);
+/* StationaryModel::new(buf): the 8 bit-position probabilities of in[0..n)
+ * (index 0 = a byte's MSB), computed on the first device, halvings of
+ * Counter::update included (src/models/counter.rs:20-26). */
+int w3_train_model(w3_ctx *ctx, const uint8_t *in, size_t n, uint16_t table[8]);
+
 /* Upper bound of w3_compress output for n input bytes. */
 size_t w3_compress_bound(size_t n, size_t block_size);
 
@@ -57,7 +75,8 @@ size_t w3_compress_bound(size_t n, size_t block_size);
  * Splits in[0..n) into ceil(n / block_size) independent blocks (block_size a
  * multiple of 4, <= 256 MiB), codes every block exactly as the reference
  * codes a file of those bytes, and writes the container
- *   "w3Bk" | u8 version=1 | u8[3] 0 | u64 BE n | u32 BE block_size | u32 BE n_blocks
+ *   "w3Bk" | u8 version | u8[3] 0 | u64 BE n | u32 BE block_size | u32 BE n_blocks
+ *   | version 2 only: 8 x u16 BE StationaryModel probabilities
  *   | n_blocks x u32 BE stream length | streams back to back
  * or, with W3_F_LEGACY, the reference's own single-stream file. */
 int w3_compress(w3_ctx *ctx, const uint8_t *in, size_t n, size_t block_size, uint32_t flags,

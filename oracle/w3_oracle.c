@@ -303,10 +303,12 @@ typedef struct {
   uint8_t alignment;
   uint64_t hist_pos;  /* ACHistory.pos  ac_history.rs:10 */
   uint64_t hist_bits; /* ACHistory.bits ac_history.rs:11 */
+  const uint16_t *table; /* StationaryModel.table  stationary.rs:9 */
 } model;
 
-static void model_init(model *m) {
+static void model_init(model *m, const uint16_t *table) {
   memset(m, 0, sizeof *m); /* ordern_entropy.rs:15-24, ac_history.rs:17-19 */
+  m->table = table ? table : W3O_BOOK1_TABLE; /* main.rs:151 */
 }
 
 static inline uint16_t model_predict(const model *m) {
@@ -324,7 +326,7 @@ static inline void model_update(model *m, unsigned bit) {
   m->hist_bits = (m->hist_bits << 1) | bit; /* ac_history.rs:24 */
   m->hist_pos += 1;                         /* ac_history.rs:25 */
   m->alignment = (uint8_t)((m->alignment + 1) & alignment_mask);
-  uint32_t hash = w3o_achash(m->hist_bits, m->hist_pos, NULL) & mask;
+  uint32_t hash = w3o_achash_ex(m->hist_bits, m->hist_pos, m->table, (int)mask_bits, NULL) & mask;
   m->ctx = (hash << ALIGNMENT_BITS) | m->alignment;
 }
 
@@ -333,10 +335,29 @@ static inline void model_update(model *m, unsigned bit) {
 
 int w3o_compress_block(const uint8_t *in, size_t n, uint8_t *out, size_t cap,
                        size_t *out_len) {
+  return w3o_compress_block_ex(in, n, NULL, out, cap, out_len);
+}
+
+/* StationaryModel::new — src/models/ac_hash/stationary.rs:14-34 */
+void w3o_stationary_new(const uint8_t *buf, size_t n, uint16_t table[8]) {
+  uint16_t model[8][2];
+  memset(model, 0, sizeof model);
+  for (size_t b = 0; b < n; b++) {
+    int i = 7;                       /* :17 */
+    for (int k = 7; k >= 0; k--) {   /* unroll_for!: MSB first, macros.rs:2-21 */
+      i = (i + 1) & 7;               /* :19 */
+      w3o_counter_update(model[i], (buf[b] >> k) & 1); /* :20 */
+    }
+  }
+  for (int i = 0; i < 8; i++) table[i] = w3o_counter_p(model[i][0], model[i][1]); /* :23-32 */
+}
+
+int w3o_compress_block_ex(const uint8_t *in, size_t n, const uint16_t *table, uint8_t *out,
+                          size_t cap, size_t *out_len) {
   if ((!in && n) || (!out && cap) || !out_len) return W3O_E_ARG;
   model *m = (model *)malloc(sizeof *m);
   if (!m) return W3O_E_ARG;
-  model_init(m);
+  model_init(m, table);
   w3o_writer w;
   writer_init(&w, out, cap);
   coder ac;
@@ -358,10 +379,15 @@ int w3o_compress_block(const uint8_t *in, size_t n, uint8_t *out, size_t cap,
 
 int w3o_decompress_block(const uint8_t *in, size_t n_in, uint8_t *out,
                          size_t n_out) {
+  return w3o_decompress_block_ex(in, n_in, NULL, out, n_out);
+}
+
+int w3o_decompress_block_ex(const uint8_t *in, size_t n_in, const uint16_t *table, uint8_t *out,
+                            size_t n_out) {
   if ((!in && n_in) || (!out && n_out)) return W3O_E_ARG;
   model *m = (model *)malloc(sizeof *m);
   if (!m) return W3O_E_ARG;
-  model_init(m);
+  model_init(m, table);
   w3o_reader r;
   reader_init(&r, in, n_in);
   coder ac;
@@ -384,7 +410,7 @@ int w3o_decompress_block(const uint8_t *in, size_t n_in, uint8_t *out,
 void w3o_ctx_trace(const uint8_t *in, size_t n, uint16_t *ctx_out) {
   model *m = (model *)malloc(sizeof *m);
   if (!m) return;
-  model_init(m);
+  model_init(m, NULL);
   size_t t = 0;
   for (size_t i = 0; i < n; i++)
     for (int k = 7; k >= 0; k--) {

@@ -96,6 +96,16 @@ int w3o_compress_block(const uint8_t *in, size_t n, uint8_t *out, size_t cap,
 int w3o_decompress_block(const uint8_t *in, size_t n_in, uint8_t *out,
                          size_t n_out);
 
+/* The same two loops with another StationaryModel table (NULL = for_book1):
+ * StationaryModel::from_table — src/models/ac_hash/stationary.rs:36-38 */
+int w3o_compress_block_ex(const uint8_t *in, size_t n, const uint16_t *table, uint8_t *out,
+                          size_t cap, size_t *out_len);
+int w3o_decompress_block_ex(const uint8_t *in, size_t n_in, const uint16_t *table, uint8_t *out,
+                            size_t n_out);
+/* StationaryModel::new(buf) — src/models/ac_hash/stationary.rs:14-34: the 8
+ * bit-position probabilities of a buffer (index 0 = a byte's MSB) */
+void w3o_stationary_new(const uint8_t *buf, size_t n, uint16_t table[8]);
+
 /* Whole reference file: "w30i" + u64 BE length + stream (main.rs:14-15,95-96) */
 int w3o_compress_file(const uint8_t *in, size_t n, uint8_t *out, size_t cap,
                       size_t *out_len);

@@ -224,9 +224,20 @@ class OrderNEntropy:
         self.ctx = (h << self.nalign) | self.alignment
 
 
-def compress_block(data: bytes) -> bytes:
+def stationary_new(buf: bytes):
+    """StationaryModel::new — src/models/ac_hash/stationary.rs:14-34."""
+    model = [[0, 0] for _ in range(8)]
+    for byte in buf:
+        i = 7
+        for k in range(7, -1, -1):
+            i = (i + 1) & 7
+            counter_update(model[i], (byte >> k) & 1)
+    return tuple(counter_p(c[0], c[1]) for c in model)
+
+
+def compress_block(data: bytes, table=BOOK1) -> bytes:
     """Stream after the 12-byte header — src/main.rs:99-111."""
-    sink, coder, model = ByteSink(), Coder(), OrderNEntropy()
+    sink, coder, model = ByteSink(), Coder(), OrderNEntropy(table=table)
     for byte in data:
         for k in range(7, -1, -1):
             bit = (byte >> k) & 1
@@ -237,9 +248,9 @@ def compress_block(data: bytes) -> bytes:
     return bytes(sink.out)
 
 
-def decompress_block(stream: bytes, n_out: int) -> bytes:
+def decompress_block(stream: bytes, n_out: int, table=BOOK1) -> bytes:
     """src/main.rs:127-140."""
-    src, coder, model = BitSource(stream), Coder(), OrderNEntropy()
+    src, coder, model = BitSource(stream), Coder(), OrderNEntropy(table=table)
     coder.start_decode(src)
     out = bytearray()
     for _ in range(n_out):

@@ -71,6 +71,9 @@ def load_oracle():
     o.w3o_ac_decode_probs.argtypes = [u8p, sz, u16p, sz, C.c_void_p, sz]
     o.w3o_compress_block.argtypes = [u8p, sz, C.c_void_p, sz, C.POINTER(sz)]
     o.w3o_decompress_block.argtypes = [u8p, sz, C.c_void_p, sz]
+    o.w3o_compress_block_ex.argtypes = [u8p, sz, u16p, C.c_void_p, sz, C.POINTER(sz)]
+    o.w3o_decompress_block_ex.argtypes = [u8p, sz, u16p, C.c_void_p, sz]
+    o.w3o_stationary_new.argtypes = [u8p, sz, u16p]
     o.w3o_compress_file.argtypes = [u8p, sz, C.c_void_p, sz, C.POINTER(sz)]
     o.w3o_decompress_file.argtypes = [u8p, sz, C.c_void_p, sz, C.POINTER(sz)]
     o.w3o_ctx_trace.argtypes = [u8p, sz, u16p]
@@ -85,20 +88,27 @@ class Oracle:
     def __init__(self):
         self.lib = load_oracle()
 
-    def compress_block(self, data: bytes) -> bytes:
+    def compress_block(self, data: bytes, table=None) -> bytes:
         n = len(data)
         cap = 17 * n + 64
         out = C.create_string_buffer(cap)
         ol = C.c_size_t()
-        rc = self.lib.w3o_compress_block(data, n, out, cap, C.byref(ol))
+        t = (C.c_uint16 * 8)(*table) if table is not None else None
+        rc = self.lib.w3o_compress_block_ex(data, n, t, out, cap, C.byref(ol))
         assert rc == 0, rc
         return out.raw[: ol.value]
 
-    def decompress_block(self, stream: bytes, n_out: int) -> bytes:
+    def decompress_block(self, stream: bytes, n_out: int, table=None) -> bytes:
         out = C.create_string_buffer(max(n_out, 1))
-        rc = self.lib.w3o_decompress_block(stream, len(stream), out, n_out)
+        t = (C.c_uint16 * 8)(*table) if table is not None else None
+        rc = self.lib.w3o_decompress_block_ex(stream, len(stream), t, out, n_out)
         assert rc == 0, rc
         return out.raw[:n_out]
+
+    def stationary_new(self, data: bytes):
+        t = (C.c_uint16 * 8)()
+        self.lib.w3o_stationary_new(data, len(data), t)
+        return tuple(t)
 
     def compress_file(self, data: bytes) -> bytes:
         n = len(data)

@@ -18,6 +18,7 @@ DEFAULT_BLOCK = 1 << 20
 # every symbol include/w3_codec.h declares
 SYMBOLS = (
     "w3_ctx_create", "w3_ctx_destroy", "w3_ctx_device_count", "w3_compress_bound",
+    "w3_ctx_set_model", "w3_ctx_get_model", "w3_train_model",
     "w3_compress", "w3_decompress", "w3_decompressed_size",
     "w3_encode_device", "w3_pack_device", "w3_decode_device",
     "w3_selftest_achash", "w3_selftest_counter_p", "w3_selftest_ac_encode", "w3_selftest_ac_decode",
@@ -53,6 +54,9 @@ def load():
     lib.w3_ctx_destroy.argtypes = [vp]
     lib.w3_ctx_destroy.restype = None
     lib.w3_ctx_device_count.argtypes = [vp]
+    lib.w3_ctx_set_model.argtypes = [vp, vp]
+    lib.w3_ctx_get_model.argtypes = [vp, vp]
+    lib.w3_train_model.argtypes = [vp, u8p, sz, vp]
     lib.w3_compress_bound.argtypes = [sz, sz]
     lib.w3_compress_bound.restype = sz
     lib.w3_compress.argtypes = [vp, u8p, sz, sz, C.c_uint32, u8p, sz, C.POINTER(sz)]
@@ -113,6 +117,22 @@ class Context:
             self.handle = None
 
     __del__ = close
+
+    # ---- the StationaryModel (stationary.rs:14-46) -------------------------
+    def set_model(self, table) -> None:
+        arr = (C.c_uint16 * 8)(*table)
+        check(self.lib.w3_ctx_set_model(self.handle, C.addressof(arr)))
+
+    def get_model(self):
+        arr = (C.c_uint16 * 8)()
+        check(self.lib.w3_ctx_get_model(self.handle, C.addressof(arr)))
+        return tuple(arr)
+
+    def train_model(self, data: bytes):
+        """StationaryModel::new(buf) on the GPU."""
+        arr = (C.c_uint16 * 8)()
+        check(self.lib.w3_train_model(self.handle, _addr(data), len(data), C.addressof(arr)))
+        return tuple(arr)
 
     # ---- host-buffer API -------------------------------------------------
     def compress_bound(self, n: int, block_size: int = DEFAULT_BLOCK) -> int:

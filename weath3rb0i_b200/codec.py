@@ -32,13 +32,25 @@ class Action(enum.Enum):  # src/main.rs:17-22
     Test = "t"
 
 
-def compress(input_file, output_file, block_size: int | None = None, ctx: capi.Context | None = None) -> None:
+BOOK1 = (1, 50188, 62497, 15819, 22545, 31499, 22988, 29616)  # stationary.rs:40-42
+ENWIK7 = (752, 50314, 58928, 21421, 24680, 30788, 24297, 32530)  # stationary.rs:44-46
+
+
+def compress(input_file, output_file, block_size: int | None = None, ctx: capi.Context | None = None,
+             model="book1") -> None:
     """src/main.rs:89-113.  block_size=None writes the reference's own
     single-stream file (magic w30i) when the input fits one block, otherwise
-    the w3Bk block container with 1 MiB blocks."""
+    the w3Bk block container with 1 MiB blocks.  model: "book1" (init_model,
+    src/main.rs:151), "enwik7", "train" (StationaryModel::new on the input,
+    stationary.rs:14-34) or 8 probabilities; anything but book1 writes the
+    container, which carries the model."""
     ctx = ctx or default_context()
     with open(input_file, "rb") as f:
         data = f.read()
+    table = {"book1": BOOK1, "enwik7": ENWIK7}.get(model, model) if model != "train" else ctx.train_model(data)
+    ctx.set_model(table)
+    if tuple(table) != BOOK1:
+        block_size = block_size or capi.DEFAULT_BLOCK
     if block_size is None:
         legacy = len(data) <= capi.DEFAULT_BLOCK
         blob = ctx.compress(data, capi.DEFAULT_BLOCK, legacy=legacy)

@@ -37,7 +37,7 @@ static int cuda_fail(cudaError_t e, const char *what) {
 
 static const uint8_t MAGIC_LEGACY[4] = {'w', '3', '0', 'i'}; /* src/main.rs:14 */
 static const uint8_t MAGIC_BLOCKS[4] = {'w', '3', 'B', 'k'};
-static const size_t HDR_LEGACY = 12, HDR_BLOCKS = 24;
+static const size_t HDR_LEGACY = 12, HDR_BLOCKS = 24, HDR_MODEL = 16; /* v2 appends the 8 u16 BE probabilities */
 static const size_t MAX_BLOCK = (size_t)256 << 20;
 
 struct w3_buf {
@@ -70,10 +70,13 @@ struct w3_dev {
   uint32_t *d_flag = nullptr;
 };
 
+static const uint16_t BOOK1[8] = W3_BOOK1_TABLE; /* StationaryModel::for_book1 — stationary.rs:40-42 */
+
 struct w3_ctx {
   int n = 0;
   w3_dev d[W3_MAX_DEVICES];
-  std::mutex mu; /* one host call at a time per context */
+  uint16_t table[8]; /* the StationaryModel in force (init_model: for_book1, src/main.rs:151) */
+  std::mutex mu;     /* one host call at a time per context */
 };
 
 static void put_be32(uint8_t *p, uint32_t v) { for (int i = 0; i < 4; i++) p[i] = (uint8_t)(v >> (24 - 8 * i)); }
@@ -97,10 +100,15 @@ static int dev_init(w3_dev &d, int ordinal) {
   CK(w3_kernels_init());
   CK(cudaMalloc(&d.d_tab, sizeof(w3_hashtab)));
   CK(cudaMalloc(&d.d_flag, sizeof(uint32_t)));
+  return W3_OK;
+}
+
+/* (re)build the threshold tables of device d for a StationaryModel table */
+static int dev_build_table(w3_dev &d, const uint16_t *table) {
+  CK(cudaSetDevice(d.ordinal));
   std::vector<uint8_t> host(sizeof(w3_hashtab), 0);
   w3_hashtab *h = reinterpret_cast<w3_hashtab *>(host.data());
-  const uint16_t book1[8] = W3_BOOK1_TABLE; /* init_model — src/main.rs:151 */
-  for (int i = 0; i < 8; i++) h->table[i] = book1[i];
+  for (int i = 0; i < 8; i++) h->table[i] = table[i];
   h->max_bits = W3_HASH_BITS;
   CK(cudaMemcpyAsync(d.d_tab, h, sizeof(w3_hashtab), cudaMemcpyHostToDevice, d.stream));
   CK(w3_launch_build_table(d.d_tab, d.stream));
@@ -108,6 +116,19 @@ static int dev_init(w3_dev &d, int ordinal) {
   CK(cudaMemcpyAsync(&bad, &d.d_tab->bad, sizeof bad, cudaMemcpyDeviceToHost, d.stream));
   CK(cudaStreamSynchronize(d.stream));
   return bad ? W3_E_TABLE : W3_OK;
+}
+
+static int ctx_set_model(w3_ctx *ctx, const uint16_t *table) {
+  if (!memcmp(ctx->table, table, sizeof ctx->table)) return W3_OK;
+  for (int g = 0; g < ctx->n; g++) {
+    int rc = dev_build_table(ctx->d[g], table);
+    if (rc != W3_OK) { /* leave the context on a usable model */
+      for (int k = 0; k <= g; k++) dev_build_table(ctx->d[k], ctx->table);
+      return rc;
+    }
+  }
+  memcpy(ctx->table, table, sizeof ctx->table);
+  return W3_OK;
 }
 
 static void dev_release(w3_dev &d) {
@@ -169,8 +190,10 @@ int w3_ctx_create(const int *devices, int n_devices, w3_ctx **out) {
     if (ord < 0 || ord >= have) { w3_ctx_destroy(ctx); return W3_E_ARG; }
     ctx->n = i + 1;
     int rc = dev_init(ctx->d[i], ord);
+    if (rc == W3_OK) rc = dev_build_table(ctx->d[i], BOOK1);
     if (rc != W3_OK) { w3_ctx_destroy(ctx); return rc; }
   }
+  memcpy(ctx->table, BOOK1, sizeof ctx->table);
   *out = ctx;
   return W3_OK;
 }
@@ -182,11 +205,41 @@ void w3_ctx_destroy(w3_ctx *ctx) {
 }
 int w3_ctx_device_count(const w3_ctx *ctx) { return ctx ? ctx->n : 0; }
 
+int w3_ctx_set_model(w3_ctx *ctx, const uint16_t *table) {
+  if (!ctx || !table) return W3_E_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  return ctx_set_model(ctx, table);
+}
+
+int w3_ctx_get_model(const w3_ctx *ctx, uint16_t *table) {
+  if (!ctx || !table) return W3_E_ARG;
+  memcpy(table, ctx->table, sizeof ctx->table);
+  return W3_OK;
+}
+
+int w3_train_model(w3_ctx *ctx, const uint8_t *in, size_t n, uint16_t *table) {
+  if (!ctx || !table || (!in && n)) return W3_E_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  w3_dev &d = ctx->d[0];
+  CK(cudaSetDevice(d.ordinal));
+  const size_t n_chunks = (n + 1023) / 1024;
+  int rc;
+  if ((rc = d.in.ensure(n + 16)) != W3_OK) return rc;
+  if ((rc = d.scratch.ensure(n_chunks * 16 + 16)) != W3_OK) return rc;
+  if ((rc = d.offsets.ensure(64)) != W3_OK) return rc;
+  if (n) CK(cudaMemcpyAsync(d.in.p, in, n, cudaMemcpyHostToDevice, d.stream));
+  CK(w3_launch_train((const uint8_t *)d.in.p, n, (uint16_t *)d.scratch.p, (uint16_t *)d.offsets.p,
+                     d.sm_count, d.stream));
+  CK(cudaMemcpyAsync(table, d.offsets.p, 16, cudaMemcpyDeviceToHost, d.stream));
+  CK(cudaStreamSynchronize(d.stream));
+  return W3_OK;
+}
+
 size_t w3_compress_bound(size_t n, size_t block_size) {
   if (!block_size) block_size = W3_DEFAULT_BLOCK;
   size_t nb = (n + block_size - 1) / block_size;
   /* <= 16.001 coded bits per input bit (p >= 2^-16), + flush, per block */
-  return HDR_BLOCKS + 4 * nb + 17 * n + 8 * (nb + 1);
+  return HDR_BLOCKS + HDR_MODEL + 4 * nb + 17 * n + 8 * (nb + 1);
 }
 
 /* ---- device-resident entry points ---------------------------------------- */
@@ -297,7 +350,11 @@ int w3_compress(w3_ctx *ctx, const uint8_t *in, size_t n, size_t block_size, uin
    * in legacy form, and an empty container has zero blocks */
   const size_t nb = legacy ? 1 : (n + block_size - 1) / block_size;
   if (nb > 0xFFFFFFFFull) return W3_E_ARG;
-  const size_t hdr = legacy ? HDR_LEGACY : HDR_BLOCKS + 4 * nb;
+  /* the reference's file format has no room for a model: it implies for_book1 */
+  const bool custom = memcmp(ctx->table, BOOK1, sizeof BOOK1) != 0;
+  if (legacy && custom) return W3_E_ARG;
+  const size_t fixed = HDR_BLOCKS + (custom ? HDR_MODEL : 0);
+  const size_t hdr = legacy ? HDR_LEGACY : fixed + 4 * nb;
 
   enc_part parts[W3_MAX_DEVICES];
   for (int g = 0; g < ctx->n; g++) block_range(nb, ctx->n, g, parts[g].b0, parts[g].b1);
@@ -320,11 +377,13 @@ int w3_compress(w3_ctx *ctx, const uint8_t *in, size_t n, size_t block_size, uin
     put_be64(out + 4, (uint64_t)n); /* main.rs:96 */
   } else {
     memcpy(out, MAGIC_BLOCKS, 4);
-    out[4] = 1; out[5] = out[6] = out[7] = 0;
+    out[4] = custom ? 2 : 1; out[5] = out[6] = out[7] = 0;
     put_be64(out + 8, (uint64_t)n);
     put_be32(out + 16, (uint32_t)block_size);
     put_be32(out + 20, (uint32_t)nb);
-    uint8_t *idx = out + HDR_BLOCKS;
+    if (custom)
+      for (int i = 0; i < 8; i++) { out[HDR_BLOCKS + 2 * i] = (uint8_t)(ctx->table[i] >> 8); out[HDR_BLOCKS + 2 * i + 1] = (uint8_t)ctx->table[i]; }
+    uint8_t *idx = out + fixed;
     for (int g = 0; g < ctx->n; g++)
       for (uint32_t l : parts[g].lens) { put_be32(idx, l); idx += 4; }
   }
@@ -349,7 +408,8 @@ int w3_decompressed_size(const uint8_t *in, size_t n_in, size_t *out_len) {
     return W3_OK;
   }
   if (!memcmp(in, MAGIC_BLOCKS, 4)) {
-    if (n_in < HDR_BLOCKS || in[4] != 1) return W3_E_FORMAT;
+    if (n_in < HDR_BLOCKS || (in[4] != 1 && in[4] != 2)) return W3_E_FORMAT;
+    if (in[4] == 2 && n_in < HDR_BLOCKS + HDR_MODEL) return W3_E_FORMAT;
     *out_len = (size_t)get_be64(in + 8);
     return W3_OK;
   }
@@ -375,15 +435,22 @@ int w3_decompress(w3_ctx *ctx, const uint8_t *in, size_t n_in, uint8_t *out, siz
     nb = n ? 1 : 0;
     hdr = HDR_LEGACY;
     offs = {0, n_in - hdr};
+    if ((rc = ctx_set_model(ctx, BOOK1)) != W3_OK) return rc; /* init_model — src/main.rs:151 */
   } else {
     bs = get_be32(in + 16);
     nb = get_be32(in + 20);
     if (!bs || (bs & 3) || bs > MAX_BLOCK || nb != (n + bs - 1) / bs) return W3_E_FORMAT;
-    hdr = HDR_BLOCKS + 4 * nb;
+    const size_t fixed = HDR_BLOCKS + (in[4] == 2 ? HDR_MODEL : 0);
+    hdr = fixed + 4 * nb;
     if (n_in < hdr) return W3_E_FORMAT;
+    /* a version-2 container carries its StationaryModel; version 1 means for_book1 */
+    uint16_t table[8];
+    for (int i = 0; i < 8; i++)
+      table[i] = in[4] == 2 ? (uint16_t)((in[HDR_BLOCKS + 2 * i] << 8) | in[HDR_BLOCKS + 2 * i + 1]) : BOOK1[i];
+    if ((rc = ctx_set_model(ctx, table)) != W3_OK) return rc;
     offs.resize(nb + 1);
     uint64_t run = 0;
-    for (size_t i = 0; i < nb; i++) { offs[i] = run; run += get_be32(in + HDR_BLOCKS + 4 * i); }
+    for (size_t i = 0; i < nb; i++) { offs[i] = run; run += get_be32(in + fixed + 4 * i); }
     offs[nb] = run;
     if (hdr + run != n_in) return W3_E_FORMAT;
   }

@@ -7,7 +7,10 @@
  *
  * Extra, not in the reference: `-b <bytes>` block size (default: the
  * reference's single-stream file when the input fits 1 MiB, else 1 MiB blocks),
- * `-g <n>` number of GPUs.
+ * `-g <n>` number of GPUs, `-m book1|enwik7|train` the StationaryModel of the
+ * entropy hash (src/models/ac_hash/stationary.rs: for_book1 is what main.rs
+ * uses; `train` = StationaryModel::new on the input, as the sweep binaries do;
+ * anything but book1 writes the block container, which carries the model).
  */
 #include <dirent.h>
 #include <sys/stat.h>
@@ -52,18 +55,25 @@ static int fail(const char *what, int rc) {
 }
 static void usage() { /* main.rs:154-161 */
   fprintf(stderr,
-          "Usage: w3 [-b block_bytes] [-g gpus] <action> <path>\n"
+          "Usage: w3 [-b block_bytes] [-g gpus] [-m book1|enwik7|train] <action> <path>\n"
           "  action: c (compress) | d (decompress) | t (test)\n");
   exit(1);
 }
 
 static size_t g_block = 0;
+static std::string g_model = "book1";
 
 static int do_compress(w3_ctx *ctx, const std::string &in, const std::string &out) {
   std::vector<uint8_t> data;
   if (!read_file(in, data)) { perror(in.c_str()); return 1; }
   auto t0 = std::chrono::steady_clock::now();
-  bool legacy = g_block == 0 && data.size() <= W3_DEFAULT_BLOCK;
+  if (g_model != "book1") {
+    uint16_t table[8] = {752, 50314, 58928, 21421, 24680, 30788, 24297, 32530}; /* for_enwik7 — stationary.rs:44-46 */
+    int mrc = g_model == "train" ? w3_train_model(ctx, data.data(), data.size(), table) : W3_OK;
+    if (mrc == W3_OK) mrc = w3_ctx_set_model(ctx, table);
+    if (mrc != W3_OK) return fail("model", mrc);
+  }
+  bool legacy = g_model == "book1" && g_block == 0 && data.size() <= W3_DEFAULT_BLOCK;
   size_t bs = g_block ? g_block : W3_DEFAULT_BLOCK;
   std::vector<uint8_t> buf(data.size() + data.size() / 4 + 4096);
   size_t len = 0;
@@ -109,6 +119,7 @@ int main(int argc, char **argv) {
   for (; i + 1 < argc && argv[i][0] == '-'; i += 2) {
     if (!strcmp(argv[i], "-b")) g_block = strtoull(argv[i + 1], nullptr, 0);
     else if (!strcmp(argv[i], "-g")) gpus = atoi(argv[i + 1]);
+    else if (!strcmp(argv[i], "-m") && (!strcmp(argv[i + 1], "book1") || !strcmp(argv[i + 1], "enwik7") || !strcmp(argv[i + 1], "train"))) g_model = argv[i + 1];
     else usage();
   }
   if (argc - i != 2 || strlen(argv[i]) != 1 || !strchr("cdt", argv[i][0])) usage();

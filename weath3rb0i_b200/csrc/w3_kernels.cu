@@ -410,6 +410,96 @@ __global__ void w3_k_pack(const uint8_t *__restrict__ scratch, uint64_t stride,
 }
 
 /* ------------------------------------------------------------------------ */
+/* StationaryModel::new — src/models/ac_hash/stationary.rs:14-34             */
+/* The 8 bit-position counters of a buffer.  Counter::update halves both     */
+/* counts whenever one reaches 65535 (counter.rs:22-25), so this is not a    */
+/* histogram: the halving points are found exactly.  Pass 1 counts the ones  */
+/* of every bit position per 1 KiB chunk (any order); pass 2 walks the       */
+/* chunks in order, one warp per bit position, 32 chunks per trip while no   */
+/* halving can fall inside them and byte by byte where one does.             */
+
+#define W3_TRAIN_CHUNK 1024u
+
+__global__ void w3_k_bitpos_counts(const uint8_t *__restrict__ in, uint64_t n,
+                                   uint16_t *__restrict__ cnt /*[chunks][8]*/) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t n_chunks = (n + W3_TRAIN_CHUNK - 1) / W3_TRAIN_CHUNK;
+  const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t chunk = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < n_chunks; chunk += warps) {
+    const uint64_t base = chunk * W3_TRAIN_CHUNK + lane * 32u;
+    uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (uint32_t wd = 0; wd < 8; wd++) {
+      const uint64_t at = base + wd * 4u;
+      uint32_t v = 0;
+      if (at + 4 <= n) v = __ldg(reinterpret_cast<const uint32_t *>(in + at));
+      else for (uint32_t b = 0; b < 4 && at + b < n; b++) v |= (uint32_t)in[at + b] << (8u * b);
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc[j] += __popc(v & (0x80808080u >> j)); /* j = 0: a byte's MSB */
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      for (uint32_t d = 16; d; d >>= 1) acc[j] += __shfl_xor_sync(FULL, acc[j], d);
+    if (lane < 8) {
+      uint32_t mine = acc[0];
+#pragma unroll
+      for (int j = 1; j < 8; j++) mine = lane == (uint32_t)j ? acc[j] : mine;
+      cnt[chunk * 8u + lane] = (uint16_t)mine;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) w3_k_stationary_scan(const uint8_t *__restrict__ in, uint64_t n,
+                                                            const uint16_t *__restrict__ cnt,
+                                                            uint16_t *__restrict__ table /*[8]*/) {
+  const uint32_t j = threadIdx.x >> 5, lane = threadIdx.x & 31u; /* warp j = bit position j */
+  const uint64_t n_chunks = (n + W3_TRAIN_CHUNK - 1) / W3_TRAIN_CHUNK;
+  uint32_t c0 = 0, c1 = 0; /* Counter { data: [c0, c1] } — counter.rs:4-11 */
+  auto update = [&](uint32_t bit) { /* Counter::update — counter.rs:20-26 */
+    uint32_t slot = w3_counter_update(c0 | (c1 << 16), bit);
+    c0 = slot & 0xFFFFu;
+    c1 = slot >> 16;
+  };
+  uint64_t cursor = 0;
+  while (cursor < n_chunks) {
+    const uint64_t idx = cursor + lane;
+    const bool valid = idx < n_chunks;
+    const uint32_t len = valid ? (uint32_t)(n - idx * W3_TRAIN_CHUNK < W3_TRAIN_CHUNK ? n - idx * W3_TRAIN_CHUNK : W3_TRAIN_CHUNK) : 0u;
+    const uint32_t ones = valid ? cnt[idx * 8u + j] : 0u;
+    uint32_t po = ones, pz = len - ones; /* inclusive prefix sums over the 32 chunks */
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+      const uint32_t uo = __shfl_up_sync(FULL, po, d), uz = __shfl_up_sync(FULL, pz, d);
+      if (lane >= d) { po += uo; pz += uz; }
+    }
+    const uint32_t hit = __ballot_sync(FULL, valid && (c1 + po >= 0xFFFFu || c0 + pz >= 0xFFFFu));
+    if (!hit) { /* no count can reach 65535 inside these chunks: plain sums */
+      c1 += __shfl_sync(FULL, po, 31);
+      c0 += __shfl_sync(FULL, pz, 31);
+      cursor += 32;
+      continue;
+    }
+    const uint32_t f = (uint32_t)__ffs((int)hit) - 1u; /* first chunk a halving may fall in */
+    if (f) { c1 += __shfl_sync(FULL, po, f - 1u); c0 += __shfl_sync(FULL, pz, f - 1u); }
+    const uint64_t chunk = cursor + f, base = chunk * W3_TRAIN_CHUNK;
+    const uint32_t clen = (uint32_t)(n - base < W3_TRAIN_CHUNK ? n - base : W3_TRAIN_CHUNK);
+    for (uint32_t r = 0; r * 32u < clen; r++) { /* 32 bytes per trip, lane = byte */
+      const uint32_t o = r * 32u + lane;
+      const bool act = o < clen;
+      const uint32_t bit = act ? ((uint32_t)in[base + o] >> (7u - j)) & 1u : 0u;
+      const uint32_t ma = __ballot_sync(FULL, act), mb = __ballot_sync(FULL, act && bit);
+      const uint32_t so = __popc(mb), sz = __popc(ma) - so;
+      if (c1 + so >= 0xFFFFu || c0 + sz >= 0xFFFFu) {
+        for (uint32_t k = 0; k < 32; k++) if ((ma >> k) & 1u) update((mb >> k) & 1u);
+      } else {
+        c1 += so;
+        c0 += sz;
+      }
+    }
+    cursor = chunk + 1;
+  }
+  if (lane == 0) table[j] = (uint16_t)w3_counter_p(c0, c1); /* stationary.rs:23-32 */
+}
+
+/* ------------------------------------------------------------------------ */
 /* self-test kernels (called through w3_selftest_* in the C ABI by tests/)   */
 
 __global__ void w3_k_hash_array(const uint64_t *bits, const uint32_t *pos, uint32_t n,
@@ -585,6 +675,13 @@ cudaError_t w3_launch_decode(const uint8_t *d_comp, const uint64_t *d_offsets, u
   uint32_t grid = (n_blocks + (uint32_t)warps - 1) / (uint32_t)warps;
   w3_decode_blocks_warp<<<grid, warps * 32, w3_dense_dec_smem_bytes(warps), s>>>(
       d_comp, d_offsets, n_blocks, block_size, n_total, d_out, d_tab);
+  return cudaGetLastError();
+}
+
+cudaError_t w3_launch_train(const uint8_t *d_in, uint64_t n, uint16_t *d_cnt, uint16_t *d_table,
+                            int sm_count, cudaStream_t s) {
+  if (n) w3_k_bitpos_counts<<<sm_count * 8, 256, 0, s>>>(d_in, n, d_cnt);
+  w3_k_stationary_scan<<<1, 256, 0, s>>>(d_in, n, d_cnt, d_table);
   return cudaGetLastError();
 }
 

@@ -25,6 +25,9 @@ cudaError_t w3_launch_decode(const uint8_t *d_comp, const uint64_t *d_offsets, u
                              uint32_t block_size, uint64_t n_total, uint8_t *d_out,
                              uint32_t *d_err, const struct w3_hashtab *d_tab, int sm_count,
                              cudaStream_t s);
+/* StationaryModel::new on the device: d_cnt needs ceil(n / 1024) * 8 u16 */
+cudaError_t w3_launch_train(const uint8_t *d_in, uint64_t n, uint16_t *d_cnt, uint16_t *d_table,
+                            int sm_count, cudaStream_t s);
 cudaError_t w3_launch_hash_array(const uint64_t *d_bits, const uint32_t *d_pos, uint32_t n,
                                  uint32_t *d_out, const struct w3_hashtab *d_tab, cudaStream_t s);
 cudaError_t w3_launch_counter_p_check(unsigned long long *d_mismatches, cudaStream_t s);

@@ -7,8 +7,10 @@ lives in w3_capi.cu (block_range) for the in-process multi-device path; this
 module is what bench.py and multi-process callers use.
 
 Container (include/w3_codec.h):
-  "w3Bk" | u8 version=1 | u8[3] 0 | u64 BE n | u32 BE block_size | u32 BE n_blocks
+  "w3Bk" | u8 version | u8[3] 0 | u64 BE n | u32 BE block_size | u32 BE n_blocks
+  | version 2 only: 8 x u16 BE StationaryModel probabilities
   | n_blocks x u32 BE stream length | streams back to back
+(this module builds and joins version-1 containers, i.e. the for_book1 model)
 """
 from __future__ import annotations
 
