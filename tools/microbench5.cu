@@ -36,15 +36,13 @@ __global__ void __launch_bounds__(384) k_dec_alone(long long *cycles, uint32_t *
     if (lane == 0) sink[warp] = n;
     return;
   }
-  uint32_t x1 = 0, x2 = 0xFFFFFFFFu, x = 0x12345678u, bp = 32, rhist = 0;
-  uint2 pair = make_uint2(0u, 0u);
+  uint32_t x1 = 0, x2 = 0xFFFFFFFFu, x = 0x12345678u, bp = 32, rhist = 0, xmid = 0;
   bool dead = false;
+  auto next_mid = [&](uint2 pr, uint32_t bit) -> uint32_t { return x1 + __umulhi(x2 - x1, (bit ? pr.y : pr.x) & 0xFFFF0000u); };
   auto step = [&](uint32_t tt, uint32_t slot) {
-    const uint32_t P = (((int32_t)rhist < 0) ? pair.y : pair.x) & 0xFFFF0000u;
     const uint32_t s1 = (slot + 1u) & (W3_CAND_RING - 1u);
-    const uint2 pair_n = w3_lds64(cand_a + s1 * (W3_NGUESS * 4u) + (rhist >> (33u - W3_SPEC_D)) * 8u);
+    uint2 pair_n = w3_lds64(cand_a + s1 * (W3_NGUESS * 4u) + (rhist >> (33u - W3_SPEC_D)) * 8u);
     const uint2 sw = w3_lds64(sring_a + ((bp >> 5) & (W3_SRING - 1u)) * 8u);
-    const uint32_t xmid = x1 + __umulhi(x2 - x1, P);
     const uint32_t bit = x <= xmid ? 1u : 0u;
     if (bit) x2 = xmid; else x1 = xmid + 1u;
     rhist = __funnelshift_r(rhist, bit, 1);
@@ -53,22 +51,53 @@ __global__ void __launch_bounds__(384) k_dec_alone(long long *cycles, uint32_t *
     const int nsh = w3_ac_renorm(x1, x2, s, k);
     const uint32_t fresh = __funnelshift_l(sw.y, sw.x, bp & 31u);
     x = __funnelshift_l(fresh, x, (uint32_t)nsh) ^ ((0u - (uint32_t)k) & 0x80000000u);
-    if (V == 1) x = x1 + ((x2 - x1) >> 1) + (bp & 3);  // keep x inside the range (synthetic stream)
+    if (V == 1) x = x1 + ((x2 - x1) >> 1) + (bp & 3);
     bp += (uint32_t)nsh;
-    pair = pair_n;
+    xmid = next_mid(pair_n, bit);
+    if (V != 3 && __builtin_expect(__any_sync(FULL, ((pair_n.x ^ (tt + 2u)) & 0xFFFFu) != 0u), 0)) {
+      pair_n = w3_pair_spin(cand_a + s1 * (W3_NGUESS * 4u) + ((rhist << 1) >> (33u - W3_SPEC_D)) * 8u, tt + 2u, abort_a);
+      xmid = next_mid(pair_n, bit);
+    }
   };
-  auto pair_ok = [&](uint32_t tt) -> bool { return (((pair.x ^ (tt + 1u)) | (pair.y ^ (tt + 1u))) & 0xFFFFu) == 0u; };
   const uint32_t nbits = 1u << 18;
+  xmid = next_mid(w3_pair_spin(cand_a, 1u, abort_a), 0u);
+  if (V == 4) {
+    /* branch-free attempts: an attempt decodes bit t iff the split point computed by the
+     * previous attempt was built from valid candidates; otherwise it only re-fetches */
+    uint32_t t = 0, ok = 1;
+    long long t0b = clock64();
+    while (t < nbits) {
+#pragma unroll
+      for (uint32_t i = 0; i < 16u; i++) {
+        const uint32_t pos_n = t + ok;                               /* position whose candidates we need next */
+        const uint32_t idx = ok ? (rhist >> (33u - W3_SPEC_D)) : ((rhist << 1) >> (33u - W3_SPEC_D));
+        const uint2 pair_n = w3_lds64(cand_a + (pos_n & (W3_CAND_RING - 1u)) * (W3_NGUESS * 4u) + idx * 8u);
+        const uint2 sw = w3_lds64(sring_a + ((bp >> 5) & (W3_SRING - 1u)) * 8u);
+        const uint32_t bit = x <= xmid ? 1u : 0u;
+        if (ok && bit) x2 = xmid;
+        if (ok && !bit) x1 = xmid + 1u;
+        rhist = ok ? __funnelshift_r(rhist, bit, 1) : rhist;
+        t += ok;
+        w3_sts(pub_a, __byte_perm(rhist, t, 0x5432));
+        int s, k;
+        const int nsh = w3_ac_renorm(x1, x2, s, k);                  /* a normalised pair renormalises to itself */
+        const uint32_t fresh = __funnelshift_l(sw.y, sw.x, bp & 31u);
+        x = __funnelshift_l(fresh, x, (uint32_t)nsh) ^ ((0u - (uint32_t)k) & 0x80000000u);
+        bp += (uint32_t)nsh;
+        xmid = x1 + __umulhi(x2 - x1, (((int32_t)rhist < 0) ? pair_n.y : pair_n.x) & 0xFFFF0000u);
+        ok = (((pair_n.x ^ (t + 1u)) & 0xFFFFu) == 0u) ? 1u : 0u;
+      }
+    }
+    long long t1b = clock64();
+    w3_sts(pub_a, 0xFFFFFFFFu);
+    if (lane == 0) { cycles[0] = t1b - t0b; sink[0] = x1 ^ x2 ^ x ^ bp ^ rhist ^ ok; }
+    return;
+  }
   long long t0 = clock64();
   for (uint32_t t = 0; t + 16u <= nbits && !dead; t += 16u) {
-    if (V != 2) { w3_sts(cons_a, bp >> 5); if ((int32_t)(w3_lds(fed_a) - ((bp >> 5) + 18u)) < 0) dead = true; }
+    if (V != 2 && V != 3 && (t & 63u) == 0u) { w3_sts(cons_a, bp >> 5); if ((int32_t)(w3_lds(fed_a) - ((bp >> 5) + 66u)) < 0) dead = true; }
 #pragma unroll
-    for (uint32_t i = 0; i < 16u; i++) {
-      if (__builtin_expect(__any_sync(FULL, !pair_ok(t + i)), 0))
-        pair = w3_pair_spin(cand_a + i * (W3_NGUESS * 4u) + ((rhist << 1) >> (33u - W3_SPEC_D)) * 8u, t + i + 1u, abort_a);
-      step(t + i, i);
-    }
-    if (V != 2 && w3_lds(abort_a)) dead = true;
+    for (uint32_t i = 0; i < 16u; i++) step(t + i, i);
   }
   long long t1 = clock64();
   w3_sts(pub_a, 0xFFFFFFFFu);
@@ -84,6 +113,8 @@ int main() {
     RUN(0, "decoder step as in the kernel (random stream)")
     RUN(1, "decoder step, x kept inside the range")
     RUN(2, "decoder step, x in range, no per-trip stream check")
+    RUN(3, "decoder step, no tag check at all (no branch in the step)")
+    RUN(4, "branch-free attempts (decode iff previous candidates were valid)")
   }
   return 0;
 }

@@ -462,28 +462,6 @@ __device__ __forceinline__ bool w3_known_wait(w3_known &kn, uint32_t need, uint3
   return true;
 }
 
-/* decoder: re-fetch the candidate pair at `pa` until both entries carry `tag`
- * (out of line: the decoder's steady state must fall through) */
-#ifdef W3_DEBUG
-__device__ unsigned long long w3_dbg_wait_cycles, w3_dbg_wait_n;
-#endif
-__device__ __noinline__ uint2 w3_pair_spin(uint32_t pa, uint32_t tag, uint32_t abort_a) {
-  uint2 pr = make_uint2(0u, 0u);
-#ifdef W3_DEBUG
-  const long long dbg_t0 = clock64();
-#endif
-  for (uint32_t spins = 0; spins < W3_SPIN_LIMIT; spins++) {
-    pr = w3_lds64(pa);
-#ifdef W3_DEBUG
-    if (((pr.x ^ tag) & 0xFFFFu) == 0u && (threadIdx.x & 31) == 0) { atomicAdd(&w3_dbg_wait_cycles, (unsigned long long)(clock64() - dbg_t0)); atomicAdd(&w3_dbg_wait_n, 1ull); }
-#endif
-    if (((pr.x ^ tag) & 0xFFFFu) == 0u) return pr;
-    if ((spins & 255u) == 255u && w3_lds(abort_a)) break;
-  }
-  w3_sts(abort_a, 1u);
-  return pr;
-}
-
 __global__ void __launch_bounds__(W3_DEC_TEAM_THREADS)
 w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restrict__ offsets,
                       uint32_t n_blocks, uint32_t block_size, uint64_t n_total,
@@ -698,35 +676,44 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
   }
 
   /* ---- decoder: decode steps only (main.rs:131-140) -------------------------
-   * The steady state is straight-line code, 16 steps per loop trip: a branch
-   * costs this lone warp 10-40 cycles of fetch and resolve, more than the
-   * arithmetic of a step (profiles/r01_v4_*).  The only conditional left per
-   * step is "are the candidates of the next bit published", whose rare side
-   * leaves for a general step loop (`slow`) that waits, and comes back at the
-   * next multiple of 16. */
+   * The steady state is straight-line code with NO conditional branch per bit:
+   * a branch (even a warp-uniform vote + predicated call, placed in the shadow
+   * of the multiply) costs this lone warp about 40 cycles, against 88 for the
+   * whole step (profiles/r01_microbench5_decoder_alone.txt).  So the loop runs
+   * ATTEMPTS, 16 per trip.  An attempt decodes bit t iff the split point the
+   * previous attempt computed was built from published candidates (`ok`);
+   * otherwise the narrowing is predicated off, the range (already normalised)
+   * renormalises to itself with a zero shift, nothing advances, and the attempt
+   * amounts to re-fetching the candidates.  Either way it ends by fetching the
+   * candidate pair of the next bit to decode and noting whether its tag was
+   * valid.  Waiting for the speculators is thus "attempts that do nothing". */
   uint8_t *dst = out + off;
   uint32_t x1 = 0, x2 = 0xFFFFFFFFu, x = 0;
   uint32_t bp = 32;   /* stream bits consumed (x holds the first 32) */
   uint32_t rhist = 0; /* decoded bits, newest highest: what the speculators hash, the
                          candidate index (its top bits) and, bit-reversed, the output */
+  uint32_t rlo = 0;   /* the 32 bits before those (output words complete mid-trip) */
   bool dead = false;
-  uint2 pair = make_uint2(0u, 0u); /* candidates of bit t for bit t-1 = 0 / 1 */
+  uint32_t xmid = 0; /* split point for bit t (lerp, arithmetic_coder.rs:81); valid iff ok */
+  uint32_t ok = 0;
   uint32_t t = 0;
 
-  /* One decode step.  Candidates for bit t+1 are fetched as a pair (both
-   * values of bit t) while bit t is decoded, so that a select is all that
-   * separates two bits; stream bits come from the staged ring.  The caller has
-   * checked the tags of `pair`. */
-  auto step = [&](uint32_t tt, uint32_t slot) {
-    const uint32_t P = (((int32_t)rhist < 0) ? pair.y : pair.x) & 0xFFFF0000u;
-    const uint32_t s1 = (slot + 1u) & (W3_CAND_RING - 1u);
-    const uint2 pair_n = w3_lds64(cand_a + s1 * (W3_NGUESS * 4u) + (rhist >> (33u - W3_SPEC_D)) * 8u);
+  auto attempt = [&]() {
+    /* candidates of the bit to decode after this attempt: bit t+1 (indexed by
+     * bits t-1.., chosen by bit t) if this attempt decodes, bit t (indexed by
+     * bits t-2.., chosen by bit t-1) if not */
+    const uint32_t idx = (ok ? rhist : (rhist << 1)) >> (33u - W3_SPEC_D);
+    const uint2 pair_n = w3_lds64(cand_a + ((t + ok) & (W3_CAND_RING - 1u)) * (W3_NGUESS * 4u) + idx * 8u);
     const uint2 sw = w3_lds64(sring_a + ((bp >> 5) & (W3_SRING - 1u)) * 8u);
-    const uint32_t xmid = x1 + __umulhi(x2 - x1, P);
     const uint32_t bit = x <= xmid ? 1u : 0u; /* arithmetic_coder.rs:82 */
-    if (bit) x2 = xmid; else x1 = xmid + 1u;
-    rhist = __funnelshift_r(rhist, bit, 1);
-    w3_sts(pub_a, __byte_perm(rhist, tt + 1u, 0x5432)); /* (t+1) << 16 | newest 16 bits */
+    if (ok && bit) x2 = xmid;
+    if (ok && !bit) x1 = xmid + 1u;
+    if (ok) {
+      rlo = __funnelshift_r(rlo, rhist, 1);
+      rhist = __funnelshift_r(rhist, bit, 1);
+    }
+    t += ok;
+    w3_sts(pub_a, __byte_perm(rhist, t, 0x5432)); /* t << 16 | newest 16 bits */
     int s, k;
     const int nsh = w3_ac_renorm(x1, x2, s, k);
     /* x <<= nsh with stream bits shifted in; of the E3 flips only the last one
@@ -734,22 +721,10 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
     const uint32_t fresh = __funnelshift_l(sw.y, sw.x, bp & 31u);
     x = __funnelshift_l(fresh, x, (uint32_t)nsh) ^ ((0u - (uint32_t)k) & 0x80000000u);
     bp += (uint32_t)nsh;
-    pair = pair_n;
-  };
-  /* do the candidates of bit tt carry position tt's tag?  Both entries of a
-   * pair are stored by neighbouring lanes of one STS (one 8-byte word, one
-   * wavefront), so they turn valid together: checking one is enough. */
-  auto pair_ok = [&](uint32_t tt) -> bool { return ((pair.x ^ (tt + 1u)) & 0xFFFFu) == 0u; };
-  /* (re)fetch bit tt's candidates until the speculator has published them */
-  auto pair_wait = [&](uint32_t tt) -> bool {
-    const uint32_t pa = cand_a + (tt & (W3_CAND_RING - 1u)) * (W3_NGUESS * 4u) + ((rhist << 1) >> (33u - W3_SPEC_D)) * 8u;
-    for (uint32_t spins = 0; spins < W3_SPIN_LIMIT; spins++) {
-      pair = w3_lds64(pa);
-      if (pair_ok(tt)) return true;
-      if (w3_lds(abort_a)) break;
-    }
-    w3_sts(abort_a, 1u);
-    return false;
+    /* the newest decoded bit picks the entry.  Both entries of a pair are stored
+     * by neighbouring lanes of one STS (one 8-byte word): one tag check covers both. */
+    xmid = x1 + __umulhi(x2 - x1, (((int32_t)rhist < 0) ? pair_n.y : pair_n.x) & 0xFFFF0000u);
+    ok = (((pair_n.x ^ (t + 1u)) & 0xFFFFu) == 0u) ? 1u : 0u;
   };
   /* make sure the staged stream reaches `words` beyond the current position */
   auto need_stream = [&](uint32_t words) -> bool {
@@ -764,47 +739,34 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
     x = w3_lds(sring_a);
   }
 #ifdef W3_DEBUG
-  long long dbg_a0 = clock64(), dbg_slow = 0, dbg_nslow = 0;
+  long long dbg_a0 = clock64(), dbg_trips = 0;
 #endif
+  uint32_t stalled = 0;
   while (t < nbits && !dead) {
-    /* 4 fast trips (64 bits, at most 62 stream words) per stream-ring check */
-    if ((t & 63u) == 0u && t + 64u <= nbits && need_stream(66u)) {
+    /* 4 trips (64 attempts, at most 62 stream words) per stream-ring check; past
+     * the block's last bit no candidates are ever published, so trailing attempts
+     * of the last trip do nothing */
+    if (!need_stream(66u)) { dead = true; break; }
+    const uint32_t t_in = t;
 #pragma unroll 1
-      for (uint32_t trip = 0; trip < 4u; trip++) {
-        /* fast trip: 16 straight-line steps; a candidate pair that is not there
-         * yet is re-fetched by an out-of-line spin (the speculators are at most
-         * a step or two behind) */
+    for (uint32_t trip = 0; trip < 4u; trip++) {
+      const uint32_t t0 = t;
 #pragma unroll
-        for (uint32_t i = 0; i < 16u; i++) {
-          /* a vote is warp-uniform: a plain predicated call, no reconvergence barrier */
-          if (__builtin_expect(__any_sync(FULL, !pair_ok(t + i)), 0))
-            pair = w3_pair_spin(cand_a + i * (W3_NGUESS * 4u) + ((rhist << 1) >> (33u - W3_SPEC_D)) * 8u,
-                                t + i + 1u, abort_a);
-          step(t + i, i);
-        }
-        t += 16u;
-        if (!(t & 16u) && lane == 0) *reinterpret_cast<uint32_t *>(dst + (t >> 5) * 4u - 4u) = w3_bswap(__brev(rhist));
+      for (uint32_t i = 0; i < 16u; i++) attempt();
+      if ((t ^ t0) & 32u) { /* a word completed t - (t & ~31) < 16 bits ago */
+        const uint32_t w = __funnelshift_l(rlo, rhist, t & 31u);
+        if (lane == 0) *reinterpret_cast<uint32_t *>(dst + (t >> 5) * 4u - 4u) = w3_bswap(__brev(w));
       }
-      if (w3_lds(abort_a)) dead = true;
-      continue;
+#ifdef W3_DEBUG
+      dbg_trips++;
+#endif
     }
-    /* general steps, up to the next multiple of 16 */
-#ifdef W3_DEBUG
-    const long long dbg_s0 = clock64(); const uint32_t dbg_t_in = t;
-#endif
-    do {
-      if (!pair_ok(t) && !pair_wait(t)) { dead = true; break; }
-      if (!need_stream(3u)) { dead = true; break; }
-      step(t, t & (W3_CAND_RING - 1u));
-      t++;
-      if ((t & 31u) == 0u && lane == 0) *reinterpret_cast<uint32_t *>(dst + (t >> 5) * 4u - 4u) = w3_bswap(__brev(rhist));
-    } while ((t & 15u) != 0u && t < nbits);
-#ifdef W3_DEBUG
-    dbg_slow += clock64() - dbg_s0; dbg_nslow += t - dbg_t_in;
-#endif
+    if (w3_lds(abort_a)) dead = true;
+    stalled = t == t_in ? stalled + 1u : 0u;
+    if (stalled > W3_SPIN_LIMIT / 64u) { w3_sts(abort_a, 1u); dead = true; }
   }
 #ifdef W3_DEBUG
-  if (blk == 0 && lane == 0) printf("[w3] A: %u bits, %.1f cycles/bit overall; %lld bits in the general loop at %.1f cycles/bit; all blocks so far: %llu pair waits, %.1f cycles each\n", nbits, (double)(clock64() - dbg_a0) / nbits, dbg_nslow, dbg_nslow ? (double)dbg_slow / dbg_nslow : 0.0, w3_dbg_wait_n, w3_dbg_wait_n ? (double)w3_dbg_wait_cycles / w3_dbg_wait_n : 0.0);
+  if (blk == 0 && lane == 0) printf("[w3] A: %u bits, %.1f cycles/bit overall; %.1f cycles/attempt, %.3f attempts/bit\n", nbits, (double)(clock64() - dbg_a0) / nbits, (double)(clock64() - dbg_a0) / (16.0 * dbg_trips), 16.0 * dbg_trips / nbits);
 #endif
   w3_sts(cons_a, 0xFFFFFFFFu); /* releases the feeder */
   if (lane == 0) {
