@@ -4,6 +4,18 @@
 #include <cstdio>
 #include "../weath3rb0i_b200/csrc/w3_kernels.cu"
 
+/* the out-of-line candidate wait the kernel used before its decoder went branch-free */
+__device__ __noinline__ uint2 w3_pair_spin(uint32_t pa, uint32_t tag, uint32_t abort_a) {
+  uint2 pr = make_uint2(0u, 0u);
+  for (uint32_t spins = 0; spins < W3_SPIN_LIMIT; spins++) {
+    pr = w3_lds64(pa);
+    if (((pr.x ^ tag) & 0xFFFFu) == 0u) return pr;
+    if ((spins & 255u) == 255u && w3_lds(abort_a)) break;
+  }
+  w3_sts(abort_a, 1u);
+  return pr;
+}
+
 template <int V>
 __global__ void __launch_bounds__(384) k_dec_alone(long long *cycles, uint32_t *sink, int spinners) {
   extern __shared__ __align__(16) uint8_t smem_raw[];

@@ -364,7 +364,7 @@ struct w3_dec_team {
   uint32_t cand[W3_CAND_RING][W3_NGUESS];   /* (Counter::p << 16) | tag for every guess of the last 6 bits;
                                                tag = (pos + 1) & 0xFFFF marks the entry as position pos's */
   uint2 sring[W3_SRING];                    /* entry i = big-endian stream words (i, i+1) */
-  uint32_t pub;                             /* (bits decoded << 16) | last 16 decoded bits, newest highest */
+  uint2 pub;                                /* x = last 32 decoded bits, newest highest; y = bits decoded (one STS.64) */
   uint32_t abort_flag;
   uint32_t fed;                             /* stream words staged so far (feeder -> decoder) */
   uint32_t cons;                            /* decoder's current stream word (decoder -> feeder); ~0 = done */
@@ -386,15 +386,26 @@ __device__ __forceinline__ uint32_t w3_dec_slot(uint32_t ctx) { return ((ctx & 7
  * bad = more than W3_FIX_THR thresholds in the cell, or a tie on the high
  * word: the caller falls back to the general (64-bit) search. */
 struct w3_fix { uint32_t r, P, e; bool bad; };
+/* the tables are constant once staged: plain (schedulable) loads by 32-bit
+ * shared address — a generic pointer costs an S2R + LEA per use on this path */
+__device__ __forceinline__ uint32_t w3_ldc16(uint32_t a) {
+  uint16_t v;
+  asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t w3_ldc32(uint32_t a) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
 __device__ __forceinline__ w3_fix w3_rank_fixed_sw(uint32_t khi, uint32_t a, uint32_t sw,
-                                                   const uint32_t *thi, const uint16_t *cell2,
-                                                   uint32_t probs_a) {
-  const uint32_t e = cell2[a * W3_NCELL2 + sw];
+                                                   uint32_t thi_a, uint32_t cell2_a, uint32_t probs_a) {
+  const uint32_t e = w3_ldc16(cell2_a + (a * W3_NCELL2 + sw) * 2u);
   const uint32_t base = e & 0xFFu;
-  const uint32_t *t = thi + a * W3_THI_ROW + base;
+  const uint32_t ta = thi_a + (a * W3_THI_ROW + base) * 4u;
   uint32_t b[W3_FIX_THR];
 #pragma unroll
-  for (int i = 0; i < W3_FIX_THR; i++) b[i] = t[i];
+  for (int i = 0; i < W3_FIX_THR; i++) b[i] = w3_ldc32(ta + (uint32_t)i * 4u);
   /* slot of context (rank << 3) | a is a * 256 + rank (w3_dec_slot); ranks past
    * 255 cannot be selected, their reads stay inside the table's padding */
   const uint32_t pa = probs_a + (a * 256u + base) * 4u;
@@ -426,41 +437,49 @@ __device__ __forceinline__ w3_fix w3_rank_fixed_sw(uint32_t khi, uint32_t a, uin
   return f;
 }
 
-/* speculator's view of the decoded prefix: K = its last 64 bits as a hash key
- * (newest bit = bit 63, as w3_key_of_history builds it), known = how many */
+/* speculator's view of the decoded prefix.  pv = the decoder's published word
+ * as last read: x = the newest 32 decoded bits (newest highest — the high word
+ * of the hash key, as w3_key_of_history builds it), y = how many are decoded.
+ * lo = the 32 bits before those as of `known` bits, i.e. the key's low word:
+ * only the rare general search needs it, so it is kept up off the critical path. */
 struct w3_known {
-  uint64_t K;
-  uint32_t known;
+  uint2 pv;
+  uint32_t lo, hi, known;
 };
-/* fold the decoder's published word into (K, known); at most 16 new bits */
-__device__ __forceinline__ void w3_known_absorb(w3_known &kn, uint32_t pv) {
-  const uint32_t delta = ((pv >> 16) - kn.known) & 0xFFFFu;
-  if (delta) {
-    kn.K = (kn.K >> delta) | ((uint64_t)((pv & 0xFFFFu) >> (16u - delta)) << (64u - delta));
-    kn.known += delta;
-  }
+/* bring (hi, lo) up to pv; at most 32 new bits */
+__device__ __forceinline__ void w3_known_absorb(w3_known &kn) {
+  kn.lo = __funnelshift_rc(kn.lo, kn.hi, kn.pv.y - kn.known);
+  kn.hi = kn.pv.x;
+  kn.known = kn.pv.y;
 }
-/* wait until at least `need` bits are known; false on abort.  The spin itself
- * is as small as it gets (the waiting warps share a scheduler with a working
- * one); the published word is folded in once, afterwards. */
-__device__ __forceinline__ bool w3_known_wait(w3_known &kn, uint32_t need, uint32_t pub_a,
-                                              uint32_t abort_a) {
-  if (kn.known >= need) return true;
-  const uint32_t want = need & 0xFFFFu;
-  uint32_t pv = w3_lds(pub_a);
-  for (uint32_t spins = 0; (int32_t)(((pv >> 16) - want) << 16) < 0; spins++) {
-    if (spins > W3_SPIN_LIMIT || ((spins & 1023u) == 1023u && w3_lds(abort_a))) {
-#ifdef W3_DEBUG
-      if ((threadIdx.x & 31) == 0) printf("[w3] known_wait timeout warp %d need %u known %u pub %08x\n", threadIdx.x >> 5, need, kn.known, w3_lds(pub_a));
-#endif
-      w3_sts(abort_a, 1u);
-      return false;
-    }
-    pv = w3_lds(pub_a);
-  }
-  w3_known_absorb(kn, pv);
-  return true;
+/* Spin until the decoder has published at least `need` bits, or W3_POLL_LIMIT
+ * polls.  Written in PTX for the `bra.uni`: every lane reads the same word, the
+ * loop cannot diverge, and saying so spares the convergence barrier the
+ * compiler would otherwise put around a loop the speculators sit in all the
+ * time (BSSY/BSYNC cost this path some 30 cycles per wait).  The caller
+ * checks the outcome — once per position, not per wait. */
+#define W3_POLL_LIMIT (1u << 22)
+__device__ __forceinline__ void w3_pub_poll(w3_known &kn, uint32_t need, uint32_t pub_a) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .u32 cnt;\n"
+      ".reg .s32 d;\n"
+      "mov.u32 cnt, 0;\n"
+      "W3_POLL:\n"
+      "ld.volatile.shared.v2.u32 {%0, %1}, [%2];\n"
+      "add.u32 cnt, cnt, 1;\n"
+      "sub.s32 d, %1, %3;\n"
+      "setp.lt.s32 p, d, 0;\n"
+      "setp.lt.and.u32 p, cnt, %4, p;\n"
+      "@p bra.uni W3_POLL;\n"
+      "}\n"
+      : "=&r"(kn.pv.x), "=&r"(kn.pv.y)
+      : "r"(pub_a), "r"(need), "n"(W3_POLL_LIMIT)
+      : "memory");
 }
+/* what the decoder publishes as its bit count when it gives up: releases every wait */
+#define W3_PUB_ABORT 0x7FFFFF00u
 
 __global__ void __launch_bounds__(W3_DEC_TEAM_THREADS)
 w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restrict__ offsets,
@@ -493,7 +512,7 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
     if (i < W3_NCTX) tm->counts[i] = 0u;
   }
   for (uint32_t i = threadIdx.x; i < W3_CAND_RING * W3_NGUESS; i += blockDim.x) (&tm->cand[0][0])[i] = 0u;
-  if (threadIdx.x == 0) { tm->pub = 0; tm->abort_flag = 0; tm->fed = 0; tm->cons = 0; }
+  if (threadIdx.x == 0) { tm->pub = make_uint2(0u, 0u); tm->abort_flag = 0; tm->fed = 0; tm->cons = 0; }
   __syncthreads();
 
   const uint32_t blk = blockIdx.x;
@@ -575,26 +594,32 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
       if (eq) r = w3_rank_of_hash(w3_achash_exact(w3_key_of_history(key), pos, st->table, (int)st->max_bits).hash);
       return r;
     };
+    const uint32_t thi_a = w3_saddr(st->thi), cell2_a = w3_saddr(st->cell2);
     w3_known kn;
-    kn.K = 0;
-    kn.known = 0;
+    kn.pv = make_uint2(0u, 0u);
+    kn.lo = kn.hi = kn.known = 0;
     uint32_t ctx_m8[W3_GPL]; /* this lane's context guesses for pos-8 */
 #pragma unroll
     for (uint32_t i = 0; i < W3_GPL; i++) ctx_m8[i] = W3_CTX0_RANKED;
 #ifdef W3_DEBUG
     long long dbg_wait = 0, dbg_work = 0, dbg_n = 0, dbg_look = 0, dbg_pub = 0, dbg_fall = 0;
 #endif
+    /* The loop body is straight-line code up to the publishing store: waits are
+     * uniform PTX loops, their outcome is checked once per position (`late`),
+     * the counter commit is a same-value store by every lane (no lane-0 branch,
+     * and program order makes it visible to this lane's own lookups). */
     for (uint32_t pos = j; pos < nbits; pos += W3_SPEC_WARPS) {
+      uint32_t late = 0;
       /* adapt (main.rs:136 -> ordern_entropy.rs:32-34) for position q = pos-8,
        * whose counter this warp owns.  Its context — the guess that came true —
        * is known one bit before bit q itself: both outcomes are prepared then,
        * and committed with a select when bit q arrives. */
       if (pos >= 8u) {
         const uint32_t q = pos - 8u;
-        if (!w3_known_wait(kn, q, pub_a, abort_a)) return; /* bits < q */
-        /* bits q-D..q-1 are the newest ones of K, q-1 highest: rotate it down into the guess index */
-        const uint32_t shq = 64u - kn.known + q; /* key bit position q would take */
-        const uint32_t vq = (uint32_t)(kn.K >> (shq - W3_SPEC_D)) & (W3_NGUESS - 1u);
+        w3_pub_poll(kn, q, pub_a); /* bits < q */
+        late |= kn.pv.y - q;
+        /* bits q-D..q-1, q-1 highest, rotated into the guess index (newest = bit 0) */
+        const uint32_t vq = (kn.pv.x << ((kn.pv.y - q) & 31u)) >> (32u - W3_SPEC_D);
         const uint32_t hq = ((vq << 1) & (W3_NGUESS - 1u)) | (vq >> (W3_SPEC_D - 1u));
         uint32_t cq = __shfl_sync(FULL, ctx_m8[0], hq & 31u);
 #pragma unroll
@@ -607,13 +632,11 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
         const uint32_t nv0 = w3_counter_update(old, 0u), nv1 = w3_counter_update(old, 1u);
         const uint32_t np0 = w3_counter_p(nv0 & 0xFFFFu, nv0 >> 16) << 16;
         const uint32_t np1 = w3_counter_p(nv1 & 0xFFFFu, nv1 >> 16) << 16;
-        if (!w3_known_wait(kn, q + 1u, pub_a, abort_a)) return; /* bit q */
-        const uint32_t bq = (uint32_t)(kn.K >> (64u - kn.known + q)) & 1u;
-        if (lane == 0) {
-          w3_sts(counts_a + sq, bq ? nv1 : nv0);
-          w3_sts(probs_a + sq, bq ? np1 : np0);
-        }
-        __syncwarp();
+        w3_pub_poll(kn, q + 1u, pub_a); /* bit q */
+        late |= kn.pv.y - q - 1u;
+        const uint32_t bq = (kn.pv.x << ((kn.pv.y - q - 1u) & 31u)) >> 31;
+        w3_sts(counts_a + sq, bq ? nv1 : nv0);
+        w3_sts(probs_a + sq, bq ? np1 : np0);
       }
       /* predict for position pos under this lane's guesses, once bit pos-D-1
        * is known (pos-D bits) */
@@ -621,50 +644,58 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
 #ifdef W3_DEBUG
       const long long dbg_t0 = clock64();
 #endif
-      if (!w3_known_wait(kn, need, pub_a, abort_a)) return;
+      w3_pub_poll(kn, need, pub_a);
+      late |= kn.pv.y - need;
 #ifdef W3_DEBUG
       const long long dbg_t1 = clock64();
 #endif
-      /* drop what is known beyond bit pos-D-1; for pos < D that is everything */
-      const uint32_t extra = kn.known + W3_SPEC_D - pos;
-      const uint64_t kb = (kn.K << extra) >> W3_SPEC_D;
-      const uint32_t kbhi = (uint32_t)(kb >> 32);
+      /* The fixed-latency lookup needs only the key's high word, which comes
+       * straight from the published history: drop what is known beyond bit
+       * pos-D-1 (for pos < D that is everything), make room for the guess. */
+      const uint32_t extra = kn.pv.y + W3_SPEC_D - pos;
+      const uint32_t kbhi = (kn.pv.x << (extra & 31u)) >> W3_SPEC_D;
       w3_fix f[W3_GPL];
       bool any_bad = pos == 0u;
 #pragma unroll
       for (uint32_t i = 0; i < W3_GPL; i++) {
         const uint32_t khi = kbhi | ghi[i];
-        f[i] = w3_rank_fixed_sw(khi, pos & 7u, w3_cell2_swizzle(khi >> (32u - W3_PB2)), st->thi, st->cell2, probs_a);
+        f[i] = w3_rank_fixed_sw(khi, pos & 7u, w3_cell2_swizzle(khi >> (32u - W3_PB2)), thi_a, cell2_a, probs_a);
         any_bad |= f[i].bad;
       }
+      /* publish first: the tag in the low half makes each entry self-validating
+       * (neither a flag nor a fence is needed), and a lane whose lookup declined
+       * stores a tag that cannot match, so the decoder simply sees "not yet" */
+      const uint32_t tag = (pos + 1u) & 0xFFFFu;
+      const uint32_t slot_a = cand_a + (pos & (W3_CAND_RING - 1u)) * (W3_NGUESS * 4u) + lane * 4u;
+#pragma unroll
+      for (uint32_t i = 0; i < W3_GPL; i++)
+        w3_sts(slot_a + i * 128u, f[i].P | (tag ^ (f[i].bad || pos == 0u ? 1u : 0u)));
 #ifdef W3_DEBUG
+      const long long dbg_t2 = clock64();
       if (__any_sync(FULL, any_bad)) dbg_fall++;
 #endif
-      if (any_bad) { /* rare, and the only branch of the lookup */
+      /* a wait that gave up, or the decoder's abort mark (bit 30 of a difference) */
+      if (__builtin_expect((late >> 30) != 0u, 0)) {
+#ifdef W3_DEBUG
+        if (lane == 0) printf("[w3] speculator warp %u gives up at pos %u (pub %u)\n", warp, pos, kn.pv.y);
+#endif
+        w3_sts(abort_a, 1u);
+        return;
+      }
+      w3_known_absorb(kn);
+      if (any_bad) { /* rare; the general search, and the entry published again */
+        /* key without the guessed bits: 64-bit history shifted as kbhi was */
+        const uint64_t kb = ((((uint64_t)kn.hi << 32) | kn.lo) << (extra & 63u)) >> W3_SPEC_D;
 #pragma unroll
         for (uint32_t i = 0; i < W3_GPL; i++) {
           if (f[i].bad) f[i].r = rank_slow(kb | ((uint64_t)ghi[i] << 32), pos, f[i].e);
           if (pos == 0u) f[i].r = W3_CTX0_RANKED >> W3_ALIGN_BITS;
           f[i].P = w3_lds(probs_a + w3_dec_slot((f[i].r << W3_ALIGN_BITS) | (pos & 7u)) * 4u);
+          w3_sts(slot_a + i * 128u, f[i].P | tag);
         }
       }
-#ifdef W3_DEBUG
-      const long long dbg_t2 = clock64() + (f[0].P & 0);
-#endif
-      /* publish: the tag in the low half makes each entry self-validating, so
-       * neither a flag nor a fence is needed */
-      const uint32_t tag = (pos + 1u) & 0xFFFFu;
-      const uint32_t slot = pos & (W3_CAND_RING - 1u);
 #pragma unroll
-      for (uint32_t i = 0; i < W3_GPL; i++) {
-        w3_sts(cand_a + slot * (W3_NGUESS * 4u) + i * 128u + lane * 4u, f[i].P | tag);
-        ctx_m8[i] = (f[i].r << W3_ALIGN_BITS) | (pos & 7u);
-      }
-      /* nothing to do until bit pos-1 is known, about four decode steps away:
-       * stay off the shared-memory pipe the decoder depends on */
-#if W3_SPEC_NAP_NS > 0
-      __nanosleep(W3_SPEC_NAP_NS);
-#endif
+      for (uint32_t i = 0; i < W3_GPL; i++) ctx_m8[i] = (f[i].r << W3_ALIGN_BITS) | (pos & 7u);
 #ifdef W3_DEBUG
       dbg_wait += dbg_t1 - dbg_t0; dbg_work += clock64() - dbg_t1; dbg_n++; dbg_look += dbg_t2 - dbg_t1; dbg_pub += clock64() - dbg_t2;
 #endif
@@ -703,7 +734,7 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
      * bits t-1.., chosen by bit t) if this attempt decodes, bit t (indexed by
      * bits t-2.., chosen by bit t-1) if not */
     const uint32_t idx = (ok ? rhist : (rhist << 1)) >> (33u - W3_SPEC_D);
-    const uint2 pair_n = w3_lds64(cand_a + ((t + ok) & (W3_CAND_RING - 1u)) * (W3_NGUESS * 4u) + idx * 8u);
+    const uint32_t pair_a = cand_a + ((t + ok) & (W3_CAND_RING - 1u)) * (W3_NGUESS * 4u) + idx * 8u;
     const uint2 sw = w3_lds64(sring_a + ((bp >> 5) & (W3_SRING - 1u)) * 8u);
     const uint32_t bit = x <= xmid ? 1u : 0u; /* arithmetic_coder.rs:82 */
     if (ok && bit) x2 = xmid;
@@ -713,7 +744,10 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
       rhist = __funnelshift_r(rhist, bit, 1);
     }
     t += ok;
-    w3_sts(pub_a, __byte_perm(rhist, t, 0x5432)); /* t << 16 | newest 16 bits */
+    w3_sts64(pub_a, make_uint2(rhist, t));
+    /* fetched as late as the renormalisation's latency hides: every cycle here
+     * is a cycle more for the speculators */
+    const uint2 pair_n = w3_lds64(pair_a);
     int s, k;
     const int nsh = w3_ac_renorm(x1, x2, s, k);
     /* x <<= nsh with stream bits shifted in; of the E3 flips only the last one
@@ -721,10 +755,12 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
     const uint32_t fresh = __funnelshift_l(sw.y, sw.x, bp & 31u);
     x = __funnelshift_l(fresh, x, (uint32_t)nsh) ^ ((0u - (uint32_t)k) & 0x80000000u);
     bp += (uint32_t)nsh;
-    /* the newest decoded bit picks the entry.  Both entries of a pair are stored
-     * by neighbouring lanes of one STS (one 8-byte word): one tag check covers both. */
-    xmid = x1 + __umulhi(x2 - x1, (((int32_t)rhist < 0) ? pair_n.y : pair_n.x) & 0xFFFF0000u);
-    ok = (((pair_n.x ^ (t + 1u)) & 0xFFFFu) == 0u) ? 1u : 0u;
+    /* the newest decoded bit picks the entry; its own tag says whether it is
+     * the published candidate of bit t (a speculator lane whose fixed lookup
+     * declined publishes a non-matching tag first, the real entry later) */
+    const uint32_t sel = ((int32_t)rhist < 0) ? pair_n.y : pair_n.x;
+    xmid = x1 + __umulhi(x2 - x1, sel & 0xFFFF0000u);
+    ok = (((sel ^ (t + 1u)) & 0xFFFFu) == 0u) ? 1u : 0u;
   };
   /* make sure the staged stream reaches `words` beyond the current position */
   auto need_stream = [&](uint32_t words) -> bool {
@@ -769,6 +805,7 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
   if (blk == 0 && lane == 0) printf("[w3] A: %u bits, %.1f cycles/bit overall; %.1f cycles/attempt, %.3f attempts/bit\n", nbits, (double)(clock64() - dbg_a0) / nbits, (double)(clock64() - dbg_a0) / (16.0 * dbg_trips), 16.0 * dbg_trips / nbits);
 #endif
   w3_sts(cons_a, 0xFFFFFFFFu); /* releases the feeder */
+  if (dead) w3_sts64(pub_a, make_uint2(0u, W3_PUB_ABORT)); /* and, when giving up, the speculators */
   if (lane == 0) {
     const uint32_t rem = n & 3u; /* bytes after the last whole word */
     const uint32_t hist = __brev(rhist); /* newest bit lowest */
