@@ -4,4 +4,4 @@
 set -e
 cd "$(dirname "$0")/.."
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall \
-  -DW3_DEBUG -shared -o tools/libw3codec_dbg.so weath3rb0i_b200/csrc/w3_kernels.cu weath3rb0i_b200/csrc/w3_capi.cu
+  -DW3_DEBUG $W3_DBG_FLAGS -shared -o tools/libw3codec_dbg.so weath3rb0i_b200/csrc/w3_kernels.cu weath3rb0i_b200/csrc/w3_capi.cu

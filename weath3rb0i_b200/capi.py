@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libw3codec.so")
+LIB_PATH = os.environ.get("W3_LIB") or os.path.join(HERE, "libw3codec.so")  # W3_LIB: another build of the same library
 
 W3_OK, W3_E_ARG, W3_E_CAP, W3_E_MAGIC, W3_E_CUDA, W3_E_FORMAT, W3_E_TABLE = 0, -1, -2, -3, -4, -5, -6
 W3_F_LEGACY = 1

@@ -130,7 +130,10 @@ W3_HD uint32_t w3_counter_p(uint32_t c0, uint32_t c1) {
 #else
   uint32_t q = (uint32_t)((float)a * 131072.0f / (float)d);
 #endif
-  /* exact remainder of a*2^17 - q*d; |rem| < 2^19 so mod-2^32 maths is exact */
+  /* exact remainder of a*2^17 - q*d; |rem| < 2^19 so mod-2^32 maths is exact.
+   * (By the error bound the estimate is within one of the quotient and one step
+   * each way would do; that shorter form measured slower in the encoder's
+   * chain, 81.5 vs 80.9 cycles per bit, so the two-step form stays.) */
   int32_t rem = (int32_t)((a << 17) - q * d);
   if (rem < 0) { q -= 1u; rem += (int32_t)d; }
   if (rem < 0) { q -= 1u; rem += (int32_t)d; }
@@ -145,13 +148,11 @@ W3_HD uint32_t w3_counter_p_u64(uint32_t c0, uint32_t c1) {
 }
 /* Counter::update (:20-26); slot = c0 | c1 << 16 */
 W3_HD uint32_t w3_counter_update(uint32_t slot, uint32_t bit) {
-  uint32_t c0 = slot & 0xFFFFu, c1 = slot >> 16;
-  if (bit) c1 += 1u; else c0 += 1u;
-  if ((bit ? c1 : c0) == 0xFFFFu) {
-    c0 = (c0 >> 1) + (c0 & 1u);
-    c1 = (c1 >> 1) + (c1 & 1u);
-  }
-  return c0 | (c1 << 16);
+  /* both 16-bit halves at once: c <= 65534 before, so the +1 cannot carry, and
+   * (c >> 1) + (c & 1) <= 0x8000 keeps each half in its lane */
+  uint32_t v = slot + (bit ? 0x10000u : 1u);
+  if ((bit ? v >> 16 : v & 0xFFFFu) == 0xFFFFu) v = ((v >> 1) & 0x7FFF7FFFu) + (v & 0x00010001u);
+  return v;
 }
 
 /* ---- ACHistory::hash, literal — src/history/ac_history.rs:28-88 ----------- */

@@ -14,24 +14,28 @@
  *            warp 1  model: the warp-parallel predict/update of the warp kernel
  *                    (history -> threshold-table rank -> __match_any counter
  *                    resolution -> Counter::p), 32 bit positions per pass
+ *            warp 2  writer: turns the coder's (prefix, shift, pending) records
+ *                    into stream words
  *
- *   decode   warp 0   decoder: decode steps only.  For bit t it picks one of 32
- *                     prepared probabilities by its last 5 decoded bits.
- *            8 warps  speculators: warp j owns positions == j (mod 8).  For
+ *   decode   warp 0   decoder: decode steps only, branch-free ("attempts").
+ *                     For bit t it picks one of 32 prepared probabilities by
+ *                     its last 5 decoded bits; the entry's tag says whether it
+ *                     is there yet.  Alone on scheduler 0.
+ *            16 warps speculators: warp j owns positions == j (mod 16).  For
  *                     position pos its 32 lanes evaluate context and
  *                     probability for all 2^5 values of bits pos-5..pos-1 as
- *                     soon as bit pos-6 is known; before that, while waiting,
- *                     it applies the counter update of position pos-8.  Two
- *                     positions that share a counter are a multiple of 8
- *                     apart, hence owned by the same warp: program order alone
- *                     keeps every counter read behind the update it needs.
- *            (warps 4, 8, 11 idle so that the decoder has scheduler 0 alone)
+ *                     soon as bit pos-6 is known (sleeping on the mbarrier of
+ *                     that bit until then), publish them, prepare the
+ *                     counter's update for either value of bit pos, and
+ *                     commit it when bit pos arrives.  Positions that share a
+ *                     counter are a multiple of 8 apart; a per-alignment
+ *                     `done` word orders the next predict behind the commit.
+ *            1 warp   feeder: stages the block's stream in shared memory
  *
- * Warps of one CTA talk through volatile shared-memory words; every wait is
- * bounded (W3_SPIN_LIMIT) and trips an abort flag instead of hanging.  Rare
- * paths (waits, stream refill, pending-bit runs) are __noinline__ so that the
- * steady-state loop is straight-line code: a taken branch costs ~20 cycles of
- * instruction fetch on this chain (profiles/r01_v3_*).
+ * Warps of one CTA talk through volatile shared-memory words and mbarriers;
+ * every wait is bounded and trips an abort flag instead of hanging.  Rare paths
+ * are out of line so that the steady-state loops are straight-line code: a
+ * branch costs a lone warp 20-40 cycles (profiles/r01_microbench5_*).
  */
 #pragma once
 
@@ -39,11 +43,10 @@
 #define W3_ENC_RING 64u /* groups of 32 bits in flight between model and coder */
 #define W3_SPEC_D 5u    /* speculated bits per position: 2^D guesses, 2^(D-5) per lane */
 #define W3_GPL (1u << (W3_SPEC_D - 5u)) /* guesses per lane */
-#define W3_SPEC_WARPS 8u
-#define W3_CAND_RING 16u
-#ifndef W3_SPEC_NAP_NS
-#define W3_SPEC_NAP_NS 0 /* tried 100 ns: nanosleep is too coarse, decode 173 -> 182 cycles/bit */
+#ifndef W3_SPEC_WARPS
+#define W3_SPEC_WARPS 16u /* speculator warps: warp j owns positions = j mod W3_SPEC_WARPS */
 #endif
+#define W3_CAND_RING 16u
 
 #define W3_ERR_OVERFLOW 1u
 #define W3_ERR_ABORT 2u
@@ -344,6 +347,7 @@ w3_encode_blocks_team(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t
 /* decode                                                                   */
 
 #define W3_SRING 128u /* stream words staged in shared memory for the decoder */
+#define W3_BIT_BARS 32u
 #define W3_NGUESS (1u << W3_SPEC_D)
 
 #define W3_THI_ROW 264u
@@ -364,13 +368,26 @@ struct w3_dec_team {
   uint32_t cand[W3_CAND_RING][W3_NGUESS];   /* (Counter::p << 16) | tag for every guess of the last 6 bits;
                                                tag = (pos + 1) & 0xFFFF marks the entry as position pos's */
   uint2 sring[W3_SRING];                    /* entry i = big-endian stream words (i, i+1) */
+  unsigned long long bars[W3_BIT_BARS];     /* mbarrier per decoded bit (mod W3_BIT_BARS): the decoder arrives, speculators sleep on it */
   uint2 pub;                                /* x = last 32 decoded bits, newest highest; y = bits decoded (one STS.64) */
   uint32_t abort_flag;
   uint32_t fed;                             /* stream words staged so far (feeder -> decoder) */
   uint32_t cons;                            /* decoder's current stream word (decoder -> feeder); ~0 = done */
+  uint32_t done[8];                         /* per alignment a: positions = a mod 8 up to done[a] have their
+                                               predecessor's counter update in place and may be predicted */
+#ifdef W3_DEBUG
+  uint32_t dbg_stamp[64];                   /* clock at which the decoder published bit count t (t & 63) */
+#endif
 };
 
-#define W3_DEC_TEAM_THREADS 384
+/* warp 0 decodes and has scheduler 0 to itself (the other warps = 0 mod 4 exit
+ * at once); the warps that are not a multiple of 4, in order: the speculators,
+ * then the feeder */
+#define W3_DEC_ROLE(warp) ((warp) - 1u - ((warp) >> 2))
+#define W3_DEC_TEAM_WARPS (W3_SPEC_WARPS + 2u + W3_SPEC_WARPS / 3u)
+#define W3_DEC_TEAM_THREADS (32u * W3_DEC_TEAM_WARPS)
+static_assert(W3_DEC_ROLE(W3_DEC_TEAM_WARPS - 1u) == W3_SPEC_WARPS && (W3_DEC_TEAM_WARPS - 1u) % 4u != 0u,
+              "the last warp must be the feeder");
 
 /* counter slot of context (rank << 3) | alignment: alignment-major, so that the
  * 32 guesses of a warp (same alignment, scattered ranks) spread over the banks */
@@ -398,25 +415,37 @@ __device__ __forceinline__ uint32_t w3_ldc32(uint32_t a) {
   asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
   return v;
 }
+/* Nearly every cell of the fine first level holds no threshold at all, a few
+ * hundred hold one, a handful up to six (w3_build_cell2) — but text keeps
+ * hitting exactly those, so the fixed-latency lookup has to cover them.  It
+ * issues all W3_FIX_THR threshold loads and W3_FIX_THR + 1 probability loads at
+ * once, each predicated on the cell's count: a lane whose cell is empty loads
+ * one probability and nothing else.  Fewer wavefronts matter: the speculators
+ * kept the shared-memory pipe 44% busy, 39% of that bank-conflict replays
+ * (profiles/r01_ncu_decode_team_v8.txt), which is latency for the decoder. */
 __device__ __forceinline__ w3_fix w3_rank_fixed_sw(uint32_t khi, uint32_t a, uint32_t sw,
                                                    uint32_t thi_a, uint32_t cell2_a, uint32_t probs_a) {
   const uint32_t e = w3_ldc16(cell2_a + (a * W3_NCELL2 + sw) * 2u);
-  const uint32_t base = e & 0xFFu;
+  const uint32_t base = e & 0xFFu, cnt = e >> 8;
   const uint32_t ta = thi_a + (a * W3_THI_ROW + base) * 4u;
-  uint32_t b[W3_FIX_THR];
-#pragma unroll
-  for (int i = 0; i < W3_FIX_THR; i++) b[i] = w3_ldc32(ta + (uint32_t)i * 4u);
-  /* slot of context (rank << 3) | a is a * 256 + rank (w3_dec_slot); ranks past
-   * 255 cannot be selected, their reads stay inside the table's padding */
+  /* slot of context (rank << 3) | a is a * 256 + rank (w3_dec_slot) */
   const uint32_t pa = probs_a + (a * 256u + base) * 4u;
-  uint32_t Pc[W3_FIX_THR + 1];
+  uint32_t b[W3_FIX_THR], Pc[W3_FIX_THR + 1];
+  Pc[0] = w3_lds(pa);
 #pragma unroll
-  for (int i = 0; i <= W3_FIX_THR; i++) Pc[i] = w3_lds(pa + (uint32_t)i * 4u);
+  for (int i = 0; i < W3_FIX_THR; i++) {
+    b[i] = 0xFFFFFFFFu; /* "greater than any key": thresholds past the cell's */
+    Pc[i + 1] = 0u;
+    if (cnt > (uint32_t)i) {
+      b[i] = w3_ldc32(ta + (uint32_t)i * 4u);
+      Pc[i + 1] = w3_lds(pa + (uint32_t)(i + 1) * 4u);
+    }
+  }
   /* thresholds ascend: the compares read 1..1 0..0, the answer is Pc[their sum].
    * Everything below is a tree, not a chain (this warp issues in order: a
    * serial count of six would delay the publishing store by ~50 cycles). */
   bool gt[W3_FIX_THR];
-  bool bad = e > (((uint32_t)W3_FIX_THR << 8) | 0xFFu);
+  bool bad = cnt > (uint32_t)W3_FIX_THR;
 #pragma unroll
   for (int i = 0; i < W3_FIX_THR; i++) {
     gt[i] = khi > b[i];
@@ -452,31 +481,42 @@ __device__ __forceinline__ void w3_known_absorb(w3_known &kn) {
   kn.hi = kn.pv.x;
   kn.known = kn.pv.y;
 }
-/* Spin until the decoder has published at least `need` bits, or W3_POLL_LIMIT
- * polls.  Written in PTX for the `bra.uni`: every lane reads the same word, the
- * loop cannot diverge, and saying so spares the convergence barrier the
- * compiler would otherwise put around a loop the speculators sit in all the
- * time (BSSY/BSYNC cost this path some 30 cycles per wait).  The caller
- * checks the outcome — once per position, not per wait. */
-#define W3_POLL_LIMIT (1u << 22)
-__device__ __forceinline__ void w3_pub_poll(w3_known &kn, uint32_t need, uint32_t pub_a) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      ".reg .u32 cnt;\n"
-      ".reg .s32 d;\n"
-      "mov.u32 cnt, 0;\n"
-      "W3_POLL:\n"
-      "ld.volatile.shared.v2.u32 {%0, %1}, [%2];\n"
-      "add.u32 cnt, cnt, 1;\n"
-      "sub.s32 d, %1, %3;\n"
-      "setp.lt.s32 p, d, 0;\n"
-      "setp.lt.and.u32 p, cnt, %4, p;\n"
-      "@p bra.uni W3_POLL;\n"
-      "}\n"
-      : "=&r"(kn.pv.x), "=&r"(kn.pv.y)
-      : "r"(pub_a), "r"(need), "n"(W3_POLL_LIMIT)
-      : "memory");
+/* Sleep until the decoder has decoded `need` bits, then read what it published.
+ * The decoder arrives on an mbarrier per bit (bars[bit & 31], one arrival per
+ * phase), a speculator waits for the phase of bit need-1 with try_wait: the
+ * hardware parks the warp instead of having it spin.  That matters more than
+ * the wait's own latency: spinning speculators took issue slots and
+ * shared-memory wavefronts from the working ones and from the decoder (16
+ * spinning warps doubled every lookup's duration; nanosleep in a spin loop wakes
+ * too late).  No speculator ever lags the decoder by 32 bits — the decoder
+ * needs every speculator's candidates within W3_SPEC_WARPS bits — so the phase
+ * parity (bit index / 32, mod 2) is unambiguous.
+ * Returns 0, or bit 31 set if the wait gave up (the caller's `late`). */
+#define W3_WAIT_LIMIT (1u << 20)
+__device__ __forceinline__ uint32_t w3_bits_wait(w3_known &kn, uint32_t need, uint32_t bars_a, uint32_t pub_a) {
+  uint32_t got = 1u;
+  if (need) {
+    const uint32_t k = need - 1u;
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        ".reg .u32 cnt;\n"
+        "mov.u32 cnt, 0;\n"
+        "W3_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "@p bra.uni W3_DONE;\n"
+        "add.u32 cnt, cnt, 1;\n"
+        "setp.lt.u32 q, cnt, %3;\n"
+        "@q bra.uni W3_WAIT;\n"
+        "W3_DONE:\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(got)
+        : "r"(bars_a + (k & (W3_BIT_BARS - 1u)) * 8u), "r"((k / W3_BIT_BARS) & 1u), "n"(W3_WAIT_LIMIT)
+        : "memory");
+  }
+  kn.pv = w3_lds64(pub_a);
+  return got ? 0u : 0x80000000u;
 }
 /* what the decoder publishes as its bit count when it gives up: releases every wait */
 #define W3_PUB_ABORT 0x7FFFFF00u
@@ -512,22 +552,30 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
     if (i < W3_NCTX) tm->counts[i] = 0u;
   }
   for (uint32_t i = threadIdx.x; i < W3_CAND_RING * W3_NGUESS; i += blockDim.x) (&tm->cand[0][0])[i] = 0u;
+  if (threadIdx.x < 8) tm->done[threadIdx.x] = threadIdx.x;
+  if (threadIdx.x < W3_BIT_BARS)
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(w3_saddr(&tm->bars[threadIdx.x])) : "memory");
   if (threadIdx.x == 0) { tm->pub = make_uint2(0u, 0u); tm->abort_flag = 0; tm->fed = 0; tm->cons = 0; }
   __syncthreads();
 
   const uint32_t blk = blockIdx.x;
-  /* warps 4 and 8 stay idle: scheduler 0 (warps 0, 4, 8) belongs to the decoder */
-  if (blk >= n_blocks || warp == 4 || warp == 8) return;
+  /* scheduler 0 (warps 0, 4, 8, ...) belongs to the decoder */
+  if (blk >= n_blocks || (warp != 0 && (warp & 3u) == 0u)) return;
   const uint64_t off = (uint64_t)blk * block_size;
   const uint32_t n = (uint32_t)(n_total - off < block_size ? n_total - off : block_size);
   const uint32_t nbits = n * 8u;
-  const uint32_t cand_a = w3_saddr(&tm->cand[0][0]);
-  const uint32_t pub_a = w3_saddr(&tm->pub), abort_a = w3_saddr(&tm->abort_flag);
-  const uint32_t probs_a = w3_saddr(&tm->probs[0]), counts_a = w3_saddr(&tm->counts[0]);
-  const uint32_t sring_a = w3_saddr(&tm->sring[0]);
-  const uint32_t fed_a = w3_saddr(&tm->fed), cons_a = w3_saddr(&tm->cons);
+  /* One opaque base register: left to itself the compiler re-derives every
+   * shared address from SR_CgaCtaId (an S2R, ~30 cycles) inside the loops. */
+  uint32_t tm_a = w3_saddr(tm);
+  asm volatile("mov.u32 %0, %0;" : "+r"(tm_a));
+#define W3_TM_A(field) (tm_a + (uint32_t)offsetof(w3_dec_team, field))
+  const uint32_t cand_a = W3_TM_A(cand);
+  const uint32_t pub_a = W3_TM_A(pub), abort_a = W3_TM_A(abort_flag), bars_a = W3_TM_A(bars);
+  const uint32_t probs_a = W3_TM_A(probs), counts_a = W3_TM_A(counts);
+  const uint32_t sring_a = W3_TM_A(sring);
+  const uint32_t fed_a = W3_TM_A(fed), cons_a = W3_TM_A(cons);
 
-  if (warp == 11) {
+  if (warp != 0 && W3_DEC_ROLE(warp) == W3_SPEC_WARPS) {
     /* ---- feeder: stages the block's stream in shared memory, as big-endian
      * words, zero past its end (ACReader — io.rs:18-48), so that the decoder
      * reads stream bits with one LDS and no refill branch ------------------- */
@@ -571,8 +619,9 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
   }
 
   if (warp != 0) {
-    /* ---- speculator j: positions j, j+8, j+16, … ---------------------------- */
-    const uint32_t j = warp - 1u - (warp > 4u ? 1u : 0u) - (warp > 8u ? 1u : 0u);
+    /* ---- speculator j: positions j, j + W3_SPEC_WARPS, … -------------------- */
+    const uint32_t j = W3_DEC_ROLE(warp);
+    const uint32_t done_a = W3_TM_A(done);
     /* Guess index g (W3_SPEC_D bits) of bits pos-D..pos-1: bit 0 = the newest
      * (pos-1), so the two values of the newest bit are neighbours (the decoder
      * fetches them as one pair); the bits above it are the older ones in key
@@ -594,72 +643,52 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
       if (eq) r = w3_rank_of_hash(w3_achash_exact(w3_key_of_history(key), pos, st->table, (int)st->max_bits).hash);
       return r;
     };
-    const uint32_t thi_a = w3_saddr(st->thi), cell2_a = w3_saddr(st->cell2);
+    const uint32_t thi_a = tm_a - (uint32_t)sizeof(w3_dec_tab) + (uint32_t)offsetof(w3_dec_tab, thi);
+    const uint32_t cell2_a = tm_a - (uint32_t)sizeof(w3_dec_tab) + (uint32_t)offsetof(w3_dec_tab, cell2);
     w3_known kn;
     kn.pv = make_uint2(0u, 0u);
     kn.lo = kn.hi = kn.known = 0;
-    uint32_t ctx_m8[W3_GPL]; /* this lane's context guesses for pos-8 */
-#pragma unroll
-    for (uint32_t i = 0; i < W3_GPL; i++) ctx_m8[i] = W3_CTX0_RANKED;
 #ifdef W3_DEBUG
     long long dbg_wait = 0, dbg_work = 0, dbg_n = 0, dbg_look = 0, dbg_pub = 0, dbg_fall = 0;
+    long long dbg_l1 = 0, dbg_l2 = 0, dbg_over450 = 0, dbg_over550 = 0, dbg_latepoll = 0;
+    const uint32_t dbg_stamp_a = W3_TM_A(dbg_stamp);
 #endif
-    /* The loop body is straight-line code up to the publishing store: waits are
-     * uniform PTX loops, their outcome is checked once per position (`late`),
-     * the counter commit is a same-value store by every lane (no lane-0 branch,
-     * and program order makes it visible to this lane's own lookups). */
+    /* Per position: predict (wait for bit pos-D-1, look up, publish), prepare
+     * the counter's two possible updates, commit one when bit pos arrives.  The
+     * body is straight-line code up to the publishing store: waits are uniform
+     * PTX loops whose outcome is checked once per position (`late`). */
     for (uint32_t pos = j; pos < nbits; pos += W3_SPEC_WARPS) {
-      uint32_t late = 0;
-      /* adapt (main.rs:136 -> ordern_entropy.rs:32-34) for position q = pos-8,
-       * whose counter this warp owns.  Its context — the guess that came true —
-       * is known one bit before bit q itself: both outcomes are prepared then,
-       * and committed with a select when bit q arrives. */
-      if (pos >= 8u) {
-        const uint32_t q = pos - 8u;
-        w3_pub_poll(kn, q, pub_a); /* bits < q */
-        late |= kn.pv.y - q;
-        /* bits q-D..q-1, q-1 highest, rotated into the guess index (newest = bit 0) */
-        const uint32_t vq = (kn.pv.x << ((kn.pv.y - q) & 31u)) >> (32u - W3_SPEC_D);
-        const uint32_t hq = ((vq << 1) & (W3_NGUESS - 1u)) | (vq >> (W3_SPEC_D - 1u));
-        uint32_t cq = __shfl_sync(FULL, ctx_m8[0], hq & 31u);
-#pragma unroll
-        for (uint32_t i = 1; i < W3_GPL; i++) {
-          const uint32_t ci = __shfl_sync(FULL, ctx_m8[i], hq & 31u);
-          cq = (hq >> 5) == i ? ci : cq;
-        }
-        const uint32_t sq = w3_dec_slot(cq) * 4u;
-        const uint32_t old = w3_lds(counts_a + sq);
-        const uint32_t nv0 = w3_counter_update(old, 0u), nv1 = w3_counter_update(old, 1u);
-        const uint32_t np0 = w3_counter_p(nv0 & 0xFFFFu, nv0 >> 16) << 16;
-        const uint32_t np1 = w3_counter_p(nv1 & 0xFFFFu, nv1 >> 16) << 16;
-        w3_pub_poll(kn, q + 1u, pub_a); /* bit q */
-        late |= kn.pv.y - q - 1u;
-        const uint32_t bq = (kn.pv.x << ((kn.pv.y - q - 1u) & 31u)) >> 31;
-        w3_sts(counts_a + sq, bq ? nv1 : nv0);
-        w3_sts(probs_a + sq, bq ? np1 : np0);
-      }
-      /* predict for position pos under this lane's guesses, once bit pos-D-1
-       * is known (pos-D bits) */
+      const uint32_t a = pos & 7u;
+      /* ---- predict, once pos-D bits are known ------------------------------- */
       const uint32_t need = pos > W3_SPEC_D ? pos - W3_SPEC_D : 0u;
 #ifdef W3_DEBUG
       const long long dbg_t0 = clock64();
 #endif
-      w3_pub_poll(kn, need, pub_a);
+      uint32_t late = w3_bits_wait(kn, need, bars_a, pub_a);
       late |= kn.pv.y - need;
 #ifdef W3_DEBUG
       const long long dbg_t1 = clock64();
+      const uint32_t dbg_st = w3_lds(dbg_stamp_a + (need & 63u) * 4u);
+      if (kn.pv.y > need) dbg_latepoll++;
 #endif
+      /* The counters of alignment a are adapted by whoever predicted the previous
+       * position of that alignment — with 16 warps, another warp.  Its update is
+       * in place long before it is needed here; `done` proves it (read BEFORE the
+       * probabilities; written after them, behind a fence).  The check rides along
+       * with the lookup, off its critical path: "not yet" is one more reason for
+       * the fallback below. */
+      const bool notyet = (int32_t)(w3_lds(done_a + a * 4u) - pos) < 0;
       /* The fixed-latency lookup needs only the key's high word, which comes
        * straight from the published history: drop what is known beyond bit
        * pos-D-1 (for pos < D that is everything), make room for the guess. */
       const uint32_t extra = kn.pv.y + W3_SPEC_D - pos;
       const uint32_t kbhi = (kn.pv.x << (extra & 31u)) >> W3_SPEC_D;
       w3_fix f[W3_GPL];
-      bool any_bad = pos == 0u;
+      bool any_bad = pos == 0u || notyet;
 #pragma unroll
       for (uint32_t i = 0; i < W3_GPL; i++) {
         const uint32_t khi = kbhi | ghi[i];
-        f[i] = w3_rank_fixed_sw(khi, pos & 7u, w3_cell2_swizzle(khi >> (32u - W3_PB2)), thi_a, cell2_a, probs_a);
+        f[i] = w3_rank_fixed_sw(khi, a, w3_cell2_swizzle(khi >> (32u - W3_PB2)), thi_a, cell2_a, probs_a);
         any_bad |= f[i].bad;
       }
       /* publish first: the tag in the low half makes each entry self-validating
@@ -669,11 +698,73 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
       const uint32_t slot_a = cand_a + (pos & (W3_CAND_RING - 1u)) * (W3_NGUESS * 4u) + lane * 4u;
 #pragma unroll
       for (uint32_t i = 0; i < W3_GPL; i++)
-        w3_sts(slot_a + i * 128u, f[i].P | (tag ^ (f[i].bad || pos == 0u ? 1u : 0u)));
+        w3_sts(slot_a + i * 128u, f[i].P | (tag ^ (f[i].bad || pos == 0u || notyet ? 1u : 0u)));
 #ifdef W3_DEBUG
       const long long dbg_t2 = clock64();
       if (__any_sync(FULL, any_bad)) dbg_fall++;
+      if (pos > 64u) {
+        const uint32_t l1 = (uint32_t)dbg_t1 - dbg_st, l2 = (uint32_t)dbg_t2 - dbg_st;
+        dbg_l1 += l1; dbg_l2 += l2; dbg_over450 += l2 > 450u; dbg_over550 += l2 > 550u;
+      }
 #endif
+      w3_known_absorb(kn);
+      if (any_bad) { /* rare; the general search, and the entry published again */
+        if (notyet) {
+          uint32_t spins = 0;
+          while ((int32_t)(w3_lds(done_a + a * 4u) - pos) < 0 && ++spins < W3_WAIT_LIMIT) {}
+          if (spins >= W3_WAIT_LIMIT) late |= 0x80000000u;
+        }
+        /* key without the guessed bits: 64-bit history shifted as kbhi was */
+        const uint64_t kb = ((((uint64_t)kn.hi << 32) | kn.lo) << (extra & 63u)) >> W3_SPEC_D;
+#pragma unroll
+        for (uint32_t i = 0; i < W3_GPL; i++) {
+          if (f[i].bad) f[i].r = rank_slow(kb | ((uint64_t)ghi[i] << 32), pos, f[i].e);
+          if (pos == 0u) f[i].r = W3_CTX0_RANKED >> W3_ALIGN_BITS;
+          f[i].P = w3_lds(probs_a + w3_dec_slot((f[i].r << W3_ALIGN_BITS) | a) * 4u);
+          w3_sts(slot_a + i * 128u, f[i].P | tag);
+        }
+      }
+      /* ---- prepare the adaptation (main.rs:136 -> ordern_entropy.rs:32-34) --
+       * per lane, for its own guess of the context: the counter and probability
+       * after a 0 and after a 1.  The warp has nothing else to do until bit pos
+       * is decoded. */
+      uint32_t prep_sq[W3_GPL], prep_nv0[W3_GPL], prep_nv1[W3_GPL], prep_np0[W3_GPL], prep_np1[W3_GPL];
+#pragma unroll
+      for (uint32_t i = 0; i < W3_GPL; i++) {
+        prep_sq[i] = w3_dec_slot((f[i].r << W3_ALIGN_BITS) | a) * 4u;
+        const uint32_t old = w3_lds(counts_a + prep_sq[i]);
+        prep_nv0[i] = w3_counter_update(old, 0u);
+        prep_nv1[i] = w3_counter_update(old, 1u);
+        prep_np0[i] = w3_counter_p(prep_nv0[i] & 0xFFFFu, prep_nv0[i] >> 16) << 16;
+        prep_np1[i] = w3_counter_p(prep_nv1[i] & 0xFFFFu, prep_nv1[i] >> 16) << 16;
+      }
+#ifdef W3_DEBUG
+      dbg_wait += dbg_t1 - dbg_t0; dbg_work += clock64() - dbg_t1; dbg_n++; dbg_look += dbg_t2 - dbg_t1; dbg_pub += clock64() - dbg_t2;
+#endif
+      /* ---- commit: the guess that came true and the bit are known once bit pos
+       * is decoded: one select, one shuffle per value, and a same-value store
+       * by every lane (no lane-0 branch) */
+      late |= w3_bits_wait(kn, pos + 1u, bars_a, pub_a);
+      late |= kn.pv.y - pos - 1u;
+      {
+        const uint32_t hb = kn.pv.x << ((kn.pv.y - pos - 1u) & 31u); /* bit pos on top */
+        /* bits pos-D..pos-1, pos-1 highest, rotated into the guess index (newest = bit 0) */
+        const uint32_t vq = (hb << 1) >> (32u - W3_SPEC_D);
+        const uint32_t hq = ((vq << 1) & (W3_NGUESS - 1u)) | (vq >> (W3_SPEC_D - 1u));
+        const bool bq = (int32_t)hb < 0;
+        uint32_t nv = 0, np = 0, sq = 0;
+#pragma unroll
+        for (uint32_t i = 0; i < W3_GPL; i++) {
+          const uint32_t nvi = __shfl_sync(FULL, bq ? prep_nv1[i] : prep_nv0[i], hq & 31u);
+          const uint32_t npi = __shfl_sync(FULL, bq ? prep_np1[i] : prep_np0[i], hq & 31u);
+          const uint32_t sqi = __shfl_sync(FULL, prep_sq[i], hq & 31u);
+          if (W3_GPL == 1u || (hq >> 5) == i) { nv = nvi; np = npi; sq = sqi; }
+        }
+        w3_sts(counts_a + sq, nv);
+        w3_sts(probs_a + sq, np);
+        __threadfence_block();
+        w3_sts(done_a + a * 4u, pos + 8u);
+      }
       /* a wait that gave up, or the decoder's abort mark (bit 30 of a difference) */
       if (__builtin_expect((late >> 30) != 0u, 0)) {
 #ifdef W3_DEBUG
@@ -682,25 +773,9 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
         w3_sts(abort_a, 1u);
         return;
       }
-      w3_known_absorb(kn);
-      if (any_bad) { /* rare; the general search, and the entry published again */
-        /* key without the guessed bits: 64-bit history shifted as kbhi was */
-        const uint64_t kb = ((((uint64_t)kn.hi << 32) | kn.lo) << (extra & 63u)) >> W3_SPEC_D;
-#pragma unroll
-        for (uint32_t i = 0; i < W3_GPL; i++) {
-          if (f[i].bad) f[i].r = rank_slow(kb | ((uint64_t)ghi[i] << 32), pos, f[i].e);
-          if (pos == 0u) f[i].r = W3_CTX0_RANKED >> W3_ALIGN_BITS;
-          f[i].P = w3_lds(probs_a + w3_dec_slot((f[i].r << W3_ALIGN_BITS) | (pos & 7u)) * 4u);
-          w3_sts(slot_a + i * 128u, f[i].P | tag);
-        }
-      }
-#pragma unroll
-      for (uint32_t i = 0; i < W3_GPL; i++) ctx_m8[i] = (f[i].r << W3_ALIGN_BITS) | (pos & 7u);
-#ifdef W3_DEBUG
-      dbg_wait += dbg_t1 - dbg_t0; dbg_work += clock64() - dbg_t1; dbg_n++; dbg_look += dbg_t2 - dbg_t1; dbg_pub += clock64() - dbg_t2;
-#endif
     }
 #ifdef W3_DEBUG
+    if (blk == 0 && lane == 0) printf("[w3] B warp %u: from the decoder's publish: detect %.1f, published %.1f cycles; >450: %.3f, >550: %.3f; polled late %.3f\n", warp, (double)dbg_l1 / dbg_n, (double)dbg_l2 / dbg_n, (double)dbg_over450 / dbg_n, (double)dbg_over550 / dbg_n, (double)dbg_latepoll / dbg_n);
     if (blk == 0 && lane == 0) printf("[w3] B warp %u: positions %lld, avg wait-for-bit %.1f, avg spec+publish %.1f cycles (lookups %.1f, slot+publish %.1f, warp-level fallbacks %lld)\n", warp, dbg_n, (double)dbg_wait / dbg_n, (double)dbg_work / dbg_n, (double)dbg_look / dbg_n, (double)dbg_pub / dbg_n, dbg_fall);
 #endif
     return;
@@ -729,6 +804,7 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
   uint32_t ok = 0;
   uint32_t t = 0;
 
+  const uint32_t lane0 = lane == 0u ? 1u : 0u; /* one arrival per bit */
   auto attempt = [&]() {
     /* candidates of the bit to decode after this attempt: bit t+1 (indexed by
      * bits t-1.., chosen by bit t) if this attempt decodes, bit t (indexed by
@@ -745,6 +821,17 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
     }
     t += ok;
     w3_sts64(pub_a, make_uint2(rhist, t));
+    /* wake whoever waits for bit t-1 (release: after the word above) */
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.u32 p, %1, 0;\n"
+        "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n"
+        "}\n" ::"r"(bars_a + ((t - 1u) & (W3_BIT_BARS - 1u)) * 8u), "r"(ok & lane0)
+        : "memory");
+#ifdef W3_DEBUG
+    w3_sts(W3_TM_A(dbg_stamp) + (t & 63u) * 4u, (uint32_t)clock64());
+#endif
     /* fetched as late as the renormalisation's latency hides: every cycle here
      * is a cycle more for the speculators */
     const uint2 pair_n = w3_lds64(pair_a);
