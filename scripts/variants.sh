@@ -13,6 +13,8 @@ if [ "$1" = build ]; then
       -shared -o tools/variants/$name.so weath3rb0i_b200/csrc/w3_kernels.cu weath3rb0i_b200/csrc/w3_capi.cu 2>&1 | grep -E "error" &
   done
   wait; ls tools/variants
+elif [ "$1" = dec ]; then
+  for so in tools/variants/*.so; do W3_LIB=$PWD/$so timeout 120 python scripts/exp_decode.py 2>&1 | tail -1; done
 else
   for so in tools/variants/*.so; do
     name=$(basename $so .so)

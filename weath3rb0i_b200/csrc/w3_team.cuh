@@ -47,6 +47,9 @@
 #define W3_SPEC_WARPS 16u /* speculator warps: warp j owns positions = j mod W3_SPEC_WARPS */
 #endif
 #define W3_CAND_RING 16u
+#ifndef W3_ATTEMPTS_PER_TRIP
+#define W3_ATTEMPTS_PER_TRIP 16u /* decoder: straight-line attempts per loop trip (<= 32) */
+#endif
 
 #define W3_ERR_OVERFLOW 1u
 #define W3_ERR_ABORT 2u
@@ -677,7 +680,11 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
        * probabilities; written after them, behind a fence).  The check rides along
        * with the lookup, off its critical path: "not yet" is one more reason for
        * the fallback below. */
+#ifdef W3_UNSAFE_NO_DONE /* experiment only: bounds what the done check costs */
+      const bool notyet = false;
+#else
       const bool notyet = (int32_t)(w3_lds(done_a + a * 4u) - pos) < 0;
+#endif
       /* The fixed-latency lookup needs only the key's high word, which comes
        * straight from the published history: drop what is known beyond bit
        * pos-D-1 (for pos < D that is everything), make room for the guess. */
@@ -811,6 +818,9 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
      * bits t-2.., chosen by bit t-1) if not */
     const uint32_t idx = (ok ? rhist : (rhist << 1)) >> (33u - W3_SPEC_D);
     const uint32_t pair_a = cand_a + ((t + ok) & (W3_CAND_RING - 1u)) * (W3_NGUESS * 4u) + idx * 8u;
+#ifdef W3_FETCH_EARLY
+    const uint2 pair_n = w3_lds64(pair_a);
+#endif
     const uint2 sw = w3_lds64(sring_a + ((bp >> 5) & (W3_SRING - 1u)) * 8u);
     const uint32_t bit = x <= xmid ? 1u : 0u; /* arithmetic_coder.rs:82 */
     if (ok && bit) x2 = xmid;
@@ -834,7 +844,9 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
 #endif
     /* fetched as late as the renormalisation's latency hides: every cycle here
      * is a cycle more for the speculators */
+#ifndef W3_FETCH_EARLY
     const uint2 pair_n = w3_lds64(pair_a);
+#endif
     int s, k;
     const int nsh = w3_ac_renorm(x1, x2, s, k);
     /* x <<= nsh with stream bits shifted in; of the E3 flips only the last one
@@ -861,7 +873,7 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
     if (!need_stream(3u)) dead = true;
     x = w3_lds(sring_a);
   }
-#ifdef W3_DEBUG
+#if defined(W3_DEBUG) || defined(W3_STATS) /* W3_STATS: the decoder's own counts only, no probes in the loops */
   long long dbg_a0 = clock64(), dbg_trips = 0;
 #endif
   uint32_t stalled = 0;
@@ -872,15 +884,15 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
     if (!need_stream(66u)) { dead = true; break; }
     const uint32_t t_in = t;
 #pragma unroll 1
-    for (uint32_t trip = 0; trip < 4u; trip++) {
+    for (uint32_t trip = 0; trip < 64u / W3_ATTEMPTS_PER_TRIP; trip++) {
       const uint32_t t0 = t;
 #pragma unroll
-      for (uint32_t i = 0; i < 16u; i++) attempt();
+      for (uint32_t i = 0; i < W3_ATTEMPTS_PER_TRIP; i++) attempt();
       if ((t ^ t0) & 32u) { /* a word completed t - (t & ~31) < 16 bits ago */
         const uint32_t w = __funnelshift_l(rlo, rhist, t & 31u);
         if (lane == 0) *reinterpret_cast<uint32_t *>(dst + (t >> 5) * 4u - 4u) = w3_bswap(__brev(w));
       }
-#ifdef W3_DEBUG
+#if defined(W3_DEBUG) || defined(W3_STATS)
       dbg_trips++;
 #endif
     }
@@ -888,7 +900,7 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
     stalled = t == t_in ? stalled + 1u : 0u;
     if (stalled > W3_SPIN_LIMIT / 64u) { w3_sts(abort_a, 1u); dead = true; }
   }
-#ifdef W3_DEBUG
+#if defined(W3_DEBUG) || defined(W3_STATS)
   if (blk == 0 && lane == 0) printf("[w3] A: %u bits, %.1f cycles/bit overall; %.1f cycles/attempt, %.3f attempts/bit\n", nbits, (double)(clock64() - dbg_a0) / nbits, (double)(clock64() - dbg_a0) / (16.0 * dbg_trips), 16.0 * dbg_trips / nbits);
 #endif
   w3_sts(cons_a, 0xFFFFFFFFu); /* releases the feeder */
