@@ -1,4 +1,4 @@
-"""Experiment harness: time the decode kernel alone (device-resident, 64 x 1 MiB blocks) and say
+"""Experiment harness: time the encode and decode kernels alone (device-resident, 64 x 1 MiB blocks) and say
 whether the output matched — unlike bench.py it does not stop on a mismatch, so that deliberately
 unsafe kernel variants (scripts/variants.sh, W3_LIB=...) can be timed to bound an idea's worth.
 Never a bench number."""
@@ -35,5 +35,14 @@ for _ in range(reps): dec()
 b.record(); torch.cuda.synchronize()
 ms = a.elapsed_time(b) / reps
 mhz = 1965.0
+def enc():
+    ctx.encode_device(d_in.data_ptr(), n, block, d_scratch.data_ptr(), stride, d_lens.data_ptr(), d_flag.data_ptr(), s)
+enc(); torch.cuda.synchronize()
+a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a2.record()
+for _ in range(reps): enc()
+b2.record(); torch.cuda.synchronize()
+ems = a2.elapsed_time(b2) / reps
+print(f"{os.environ.get('W3_LIB', 'default').split('/')[-1]:16s} encode {ems:8.2f} ms  {n / 1e6 / (ems / 1e3):7.2f} MB/s  ~{ems * 1e-3 * mhz * 1e6 / (block * 8):6.1f} cycles/bit @1965MHz", flush=True)
 print(f"{os.environ.get('W3_LIB', 'default').split('/')[-1]:16s} decode {ms:8.2f} ms  {n / 1e6 / (ms / 1e3):7.2f} MB/s  ~{ms * 1e-3 * mhz * 1e6 / (block * 8):6.1f} cycles/bit @1965MHz  "
       f"flag {int(d_flag.item())}  {'match' if torch.equal(d_out[:n], d_in[:n]) else 'MISMATCH'}", flush=True)

@@ -14,7 +14,7 @@ if [ "$1" = build ]; then
   done
   wait; ls tools/variants
 elif [ "$1" = dec ]; then
-  for so in tools/variants/*.so; do W3_LIB=$PWD/$so timeout 120 python scripts/exp_decode.py 2>&1 | tail -1; done
+  for so in tools/variants/*.so; do W3_LIB=$PWD/$so timeout 120 python scripts/exp_decode.py 2>&1 | tail -2; done
 else
   for so in tools/variants/*.so; do
     name=$(basename $so .so)

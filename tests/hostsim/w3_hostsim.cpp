@@ -83,11 +83,14 @@ uint32_t hs_counter_update(uint32_t slot, uint32_t bit) { return w3_counter_upda
 /* scalar encode of one block, built only from w3_core.cuh statements */
 static int g_ranked = 0; /* 1: index counters by rank, as the kernels do */
 void hs_set_ranked(int on) { g_ranked = on; }
+static int g_coder = 0; /* 1: the width-carrying coder step (w3_coder_step), as the team kernels do */
+void hs_set_coder(int on) { g_coder = on; }
 
 int hs_compress_block(const w3_hashtab *tab, const uint8_t *in, size_t n, uint8_t *out, size_t cap,
                       size_t *out_len) {
   std::vector<uint32_t> stats(W3_NCTX, 0u);
   uint32_t x1 = 0, x2 = 0xFFFFFFFFu, ctx = g_ranked ? W3_CTX0_RANKED : 0;
+  w3_coder cw = w3_coder_new();
   uint64_t hist = 0;
   w3_writer w;
   w3_writer_init(w);
@@ -106,6 +109,14 @@ int hs_compress_block(const w3_hashtab *tab, const uint8_t *in, size_t n, uint8_
       t++;
       ctx = g_ranked ? ranked_ctx(tab, hist, (uint32_t)t)
                      : (hs_hash(tab, hist, (uint32_t)t, nullptr) << 3) | (uint32_t)(t & 7u);
+      if (g_coder) {
+        uint32_t flip, x1p, x2p;
+        const int nsh = w3_coder_step(cw, bit, w3_prob32(p), flip, x1p, x2p);
+        const int s = w3_clz32_nz(x1p ^ x2p); /* the bounds' common prefix: what is emitted plainly */
+        w3_writer_step(w, x1p, s, nsh - s, store);
+        x2 = cw.x1 + cw.w;
+        continue;
+      }
       w3_ac_narrow(x1, x2, bit, w3_prob32(p));
       uint32_t pre = x1;
       int s, k;
@@ -143,6 +154,7 @@ int hs_decompress_block(const w3_hashtab *tab, const uint8_t *in, size_t n_in, u
                         size_t n_out) {
   std::vector<uint32_t> stats(W3_NCTX, 0u);
   uint32_t x1 = 0, x2 = 0xFFFFFFFFu, ctx = g_ranked ? W3_CTX0_RANKED : 0;
+  w3_coder cw = w3_coder_new();
   uint64_t hist = 0, t = 0;
   size_t bitpos = 0;
   auto take = [&](int c) -> uint32_t {
@@ -161,12 +173,21 @@ int hs_decompress_block(const w3_hashtab *tab, const uint8_t *in, size_t n_in, u
     for (int kbit = 0; kbit < 8; kbit++) {
       uint32_t slot = stats[ctx];
       uint32_t P = w3_prob32(w3_counter_p(slot & 0xFFFFu, slot >> 16));
-      uint32_t xmid = x1 + w3_umulhi(x2 - x1, P);
-      uint32_t bit = x <= xmid ? 1u : 0u;
-      if (bit) x2 = xmid; else x1 = xmid + 1;
-      int s, k;
-      int nsh = w3_ac_renorm(x1, x2, s, k);
-      if (nsh) x = ((x << nsh) | take(nsh)) ^ (k ? 0x80000000u : 0u);
+      uint32_t bit;
+      if (g_coder) { /* as the team kernel's decoder warp */
+        const uint32_t m = w3_umulhi(cw.w, P);
+        bit = (x - cw.x1) <= m ? 1u : 0u;
+        uint32_t flip;
+        const int nsh = w3_coder_renorm(cw, bit ? cw.x1 : cw.x1 + m + 1u, bit ? m : cw.w - m - 1u, flip);
+        if (nsh) x = ((x << nsh) | take(nsh)) ^ flip;
+      } else {
+        uint32_t xmid = x1 + w3_umulhi(x2 - x1, P);
+        bit = x <= xmid ? 1u : 0u;
+        if (bit) x2 = xmid; else x1 = xmid + 1;
+        int s, k;
+        int nsh = w3_ac_renorm(x1, x2, s, k);
+        if (nsh) x = ((x << nsh) | take(nsh)) ^ (k ? 0x80000000u : 0u);
+      }
       stats[ctx] = w3_counter_update(slot, bit);
       hist = (hist << 1) | bit;
       t++;

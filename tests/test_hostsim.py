@@ -133,6 +133,36 @@ def test_rank_relabelled_counters_change_nothing(libs):
         libs.hostsim.lib.hs_set_ranked(0)
 
 
+def test_width_carrying_coder_changes_nothing(libs):
+    """w3_coder_step / w3_coder_renorm (state = (x1, width), total shift from one clz — what the
+    team kernels execute) against the oracle: same streams, same decodes, truncated streams too."""
+    rnd = random.Random(17)
+    cases = [w3_corpus.generate(60000, offset=9), bytes(rnd.getrandbits(8) for _ in range(30000)),
+             b"e" * 70000, bytes(30000), b"\xff" * 30000, bytes(range(256)) * 40, b"a", b""]
+    libs.hostsim.lib.hs_set_coder(1)
+    try:
+        for data in cases:
+            c = libs.hostsim.compress_block(data)
+            assert c == libs.oracle.compress_block(data)
+            assert libs.hostsim.decompress_block(c, len(data)) == data
+            cut = c[: len(c) // 3]
+            assert libs.hostsim.decompress_block(cut, len(data)) == libs.oracle.decompress_block(cut, len(data))
+    finally:
+        libs.hostsim.lib.hs_set_coder(0)
+
+
+def test_renorm_forms_against_the_literal_loops(tmp_path):
+    """tools/renorm_check.cpp: both closed forms of the renormalisation against the loops of
+    arithmetic_coder.rs:51-62 on a few million states (the committed default run is 6e8)."""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "renorm_check")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(root, "tools", "renorm_check.cpp")])
+    out = subprocess.run([exe, "3000000"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert " 0 mismatches" in out.stdout
+
+
 def test_fixed_latency_rank_lookup(libs):
     """w3_rank_lookup_fixed (decode speculators) agrees with the general lookup
     wherever it answers, and answers almost always."""

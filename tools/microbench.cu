@@ -33,6 +33,9 @@ __global__ void k_enc(uint32_t *out, long long *cycles, uint32_t *sink) {
   const uint32_t ra = (uint32_t)__cvta_generic_to_shared(ring);
   const uint32_t lane = threadIdx.x & 31;
   uint32_t x1 = 0, x2 = 0xFFFFFFFFu;
+  w3_coder cw = w3_coder_new();
+  sts(ra + 8192 - 16, 0xFFFFFFFFu);
+  const uint32_t ones = lds(ra + 8192 - 16); /* opaque to ptxas */
   uint64_t acc = 0; uint32_t nb = 0, words = 0, rev = 0, trouble = 0;
   uint32_t *dst = out + blockIdx.x * (N_STEPS / 8 + 64);
   long long t0 = clock64();
@@ -44,6 +47,21 @@ __global__ void k_enc(uint32_t *out, long long *cycles, uint32_t *sink) {
       uint32_t vj;
       if (V == 0) { vj = (0x6000u + ((base + j) & 7) * 0x1000u) << 16 | ((base + j) & 1); }
       else { vj = v0; v0 = v1; if (j + 2 < 32) v1 = lds(ga + (j + 2) * 4); }
+      if (V == 7) { /* as the kernel's coder warp: state only, publish the bare bounds */
+        uint32_t flip, x1p, x2p;
+        (void)w3_coder_step<false>(cw, vj & 1u, vj & 0xFFFF0000u, flip, x1p, x2p, ones);
+        asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(ra + 8192 - 8), "r"(x1p), "r"(x2p) : "memory");
+        continue;
+      }
+      if (V >= 5) { /* width-carrying coder: one clz per step */
+        uint32_t flip, x1p, x2p;
+        const int n = w3_coder_step(cw, vj & 1u, vj & 0xFFFF0000u, flip, x1p, x2p);
+        if (V == 6) { /* what the writer warp needs: bounds' common prefix, its length, the total */
+          const int s6 = w3_clz32_nz((x1p ^ x2p) | 1u);
+          sts(ra + 8192 - 8, x1p); sts(ra + 8192 - 4, (uint32_t)s6 | ((uint32_t)n << 8));
+        }
+        continue;
+      }
       w3_ac_narrow(x1, x2, vj & 1u, vj & 0xFFFF0000u);
       const uint32_t pre = x1;
       int s, k;
@@ -68,7 +86,7 @@ __global__ void k_enc(uint32_t *out, long long *cycles, uint32_t *sink) {
     }
   }
   long long t1 = clock64();
-  if (threadIdx.x == 0) { cycles[blockIdx.x] = t1 - t0; sink[blockIdx.x] = x1 ^ x2 ^ (uint32_t)acc ^ nb ^ words ^ trouble ^ rev; }
+  if (threadIdx.x == 0) { cycles[blockIdx.x] = t1 - t0; sink[blockIdx.x] = x1 ^ x2 ^ (uint32_t)acc ^ nb ^ words ^ trouble ^ rev ^ cw.x1 ^ cw.w; }
 }
 
 // decode-like step: pair select, pub store, stream bits from smem ring, candidates from a smem table
@@ -84,6 +102,7 @@ __global__ void k_dec(long long *cycles, uint32_t *sink) {
   __syncthreads();
   const uint32_t ca = (uint32_t)__cvta_generic_to_shared(cand), sa = (uint32_t)__cvta_generic_to_shared(sring), pa = (uint32_t)__cvta_generic_to_shared(pub);
   uint32_t x1 = 0, x2 = 0xFFFFFFFFu, x = 0x12345678u, bp = 32, hist = 0, rhist = 0, flag_next = 2;
+  w3_coder cw = w3_coder_new();
   uint2 pair = make_uint2(0x80000000u, 0x80000000u);
   long long t0 = clock64();
   for (uint32_t t = 0; t < N_STEPS; t += 16) {
@@ -96,6 +115,21 @@ __global__ void k_dec(long long *cycles, uint32_t *sink) {
       asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(pair_n.x), "=r"(pair_n.y) : "r"(ca + s1 * 128 + (hist & 15u) * 8u) : "memory");
       if (V >= 1) flag_next = lds(pa + 8);
       asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(sw.x), "=r"(sw.y) : "r"(sa + ((bp >> 5) & 127u) * 8u) : "memory");
+      if (V == 3) { /* width-carrying decoder step */
+        const uint32_t m = __umulhi(cw.w, P);
+        const uint32_t bit = (x - cw.x1) <= m ? 1u : 0u; /* x <= x1 + m, x >= x1 always */
+        hist = (hist << 1) | bit;
+        rhist = __funnelshift_r(rhist, bit, 1);
+        sts(pa, __byte_perm(rhist, t + i + 1u, 0x5432));
+        uint32_t flip;
+        const int nsh = w3_coder_renorm(cw, bit ? cw.x1 : cw.x1 + m + 1u, bit ? m : cw.w - m - 1u, flip);
+        const uint32_t fresh = __funnelshift_l(sw.y, sw.x, bp & 31u);
+        x = __funnelshift_l(fresh, x, (uint32_t)nsh) ^ flip;
+        bp += (uint32_t)nsh;
+        pair = pair_n;
+        x = cw.x1 + (cw.w >> 1) + (bp & 1); /* keep x inside the range (synthetic stream) */
+        continue;
+      }
       const uint32_t xmid = x1 + __umulhi(x2 - x1, P);
       const uint32_t bit = x <= xmid ? 1u : 0u;
       if (bit) x2 = xmid; else x1 = xmid + 1u;
@@ -112,7 +146,7 @@ __global__ void k_dec(long long *cycles, uint32_t *sink) {
     }
   }
   long long t1 = clock64();
-  if (threadIdx.x == 0) { cycles[blockIdx.x] = t1 - t0; sink[blockIdx.x] = x1 ^ x2 ^ x ^ bp ^ hist ^ flag_next; }
+  if (threadIdx.x == 0) { cycles[blockIdx.x] = t1 - t0; sink[blockIdx.x] = x1 ^ x2 ^ x ^ bp ^ hist ^ flag_next ^ cw.x1 ^ cw.w; }
 }
 
 template <class F> void run(const char *name, F launch, long long *d_cyc, int blocks) {
@@ -136,9 +170,13 @@ int main() {
     run("enc V2 + writer, predicated st.global", [&] { k_enc<2><<<blocks, 32>>>(d_out, d_cyc, d_sink); }, d_cyc, blocks);
     run("enc V3 + writer, branch on word full", [&] { k_enc<3><<<blocks, 32>>>(d_out, d_cyc, d_sink); }, d_cyc, blocks);
     run("enc V4 + publish (pre,s,k) to smem", [&] { k_enc<4><<<blocks, 32>>>(d_out, d_cyc, d_sink); }, d_cyc, blocks);
+    run("enc V5 width-carrying step + LDS ring entries", [&] { k_enc<5><<<blocks, 32>>>(d_out, d_cyc, d_sink); }, d_cyc, blocks);
+    run("enc V6 width-carrying step + publish to smem", [&] { k_enc<6><<<blocks, 32>>>(d_out, d_cyc, d_sink); }, d_cyc, blocks);
+    run("enc V7 as the kernel: state only + publish bounds", [&] { k_enc<7><<<blocks, 32>>>(d_out, d_cyc, d_sink); }, d_cyc, blocks);
     run("dec V0 step, no flag check", [&] { k_dec<0><<<blocks, 32>>>(d_cyc, d_sink); }, d_cyc, blocks);
     run("dec V1 step + flag check branch", [&] { k_dec<1><<<blocks, 32>>>(d_cyc, d_sink); }, d_cyc, blocks);
     run("dec V2 step, x kept in range", [&] { k_dec<2><<<blocks, 32>>>(d_cyc, d_sink); }, d_cyc, blocks);
+    run("dec V3 width-carrying step, x kept in range", [&] { k_dec<3><<<blocks, 32>>>(d_cyc, d_sink); }, d_cyc, blocks);
   }
   return 0;
 }

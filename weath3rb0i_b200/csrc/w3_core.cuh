@@ -119,6 +119,109 @@ W3_HD int w3_ac_renorm(uint32_t &x1, uint32_t &x2, int &s, int &k) {
   return n;
 }
 
+/* (hi:lo) >> min(sh, 32), low word — __funnelshift_rc */
+W3_HD uint32_t w3_fsr_clamp(uint32_t lo, uint32_t hi, uint32_t sh) {
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_rc(lo, hi, sh);
+#else
+  if (sh > 32u) sh = 32u;
+  return (uint32_t)(((((uint64_t)hi) << 32) | lo) >> sh);
+#endif
+}
+
+/* The coder's state as (x1, w = x2 - x1), and both renormalisation loops by
+ * their TOTAL shift, found with one count-leading-zeros of the width instead of
+ * two chained ones over the bounds (the closed form above): 54 instead of 80
+ * cycles of dependent latency per coded bit.
+ *
+ * Every shift of either loop (arithmetic_coder.rs:51-62) maps the width to
+ * 2w + 1, and either loop runs only while w < 2^31; a state both loops have
+ * left has w > 2^30 (its bounds straddle the midpoint and are not both inside
+ * the middle half).  So with j0 = clz(w) the state after j0 shifts is surely
+ * final, the one after j0 - 2 surely not, and the total is j0 - 1 or j0.  The
+ * state after j = j0 - 1 shifts is final iff its bounds' top bits differ
+ * (the plain shifts are over) and their next bits are not (1, 0) (no further
+ * E3 shift) — read off the RAW shifted bounds, whose top bits are the pair an
+ * E3 shift would have dropped: (0,1) if none happened, (1,0) otherwise, which
+ * is also the decoder's "flip the top bit of x" (arithmetic_coder.rs:98-102).
+ * Checked against the literal loops on 5.9e8 states (tests/hostsim, and
+ * tools/renorm_check.cpp).  Requires w >= 1.
+ *
+ * narrow (:43-49) + renormalise; returns the total shift, *flip = 0x80000000
+ * iff an E3 shift happened; x1p/x2p = the bounds after narrowing, before the
+ * shifts (what the encoder's writer needs). */
+struct w3_coder {
+  uint32_t x1, w;
+};
+W3_HD w3_coder w3_coder_new() { return w3_coder{0u, 0xFFFFFFFFu}; }
+/* `ones` = 0xFFFFFFFF: a caller in a tight loop keeps it in a register the
+ * compiler cannot re-materialise (it otherwise spends a move per use).
+ * kNeedShift = false: the caller wants the new state only (the encoder's coder
+ * warp: every instruction of a lone warp costs 2.3-2.9 cycles). */
+template <bool kNeedShift = true>
+W3_HD int w3_coder_renorm(w3_coder &c, uint32_t nx1, uint32_t nw, uint32_t &flip, uint32_t ones = 0xFFFFFFFFu) {
+  const uint32_t nx2 = nx1 + nw;
+  const uint32_t sh = 33u - (uint32_t)w3_clz32_nz(nw); /* 64-bit right shift that leaves j = max(j0-1, 0) */
+  uint32_t a = w3_fsr_clamp(0u, nx1, sh), wa = w3_fsr_clamp(ones, nw, sh); /* after j shifts */
+  const uint32_t b = w3_fsr_clamp(ones, nx2, sh);
+  /* final after j shifts: top bits differ, next bits are not (1, 0); else one more */
+  uint32_t fin;
+#if defined(__CUDA_ARCH__)
+  /* spelled out: the compiler turns the C form into six instructions, this is
+   * LOP3 (with predicate), LOP3, ISETP and two predicated updates */
+  if (kNeedShift) {
+    asm("{\n"
+        ".reg .pred p, q;\n"
+        ".reg .b32 y, z;\n"
+        "lop3.b32 z, %0, %3, 0x40000000, 0x20;\n" /* a & ~b & bit 30 */
+        "xor.b32 y, %0, %3;\n"
+        "setp.ne.u32 q, z, 0;\n"
+        "setp.lt.and.s32 p, y, 0, !q;\n"
+        "@!p add.u32 %0, %0, %0;\n"
+        "@!p mad.lo.u32 %1, %1, 2, 1;\n"
+        "selp.u32 %2, 1, 0, p;\n"
+        "}\n"
+        : "+r"(a), "+r"(wa), "=r"(fin)
+        : "r"(b));
+  } else {
+    asm("{\n"
+        ".reg .pred p, q;\n"
+        ".reg .b32 y, z;\n"
+        "lop3.b32 z, %0, %2, 0x40000000, 0x20;\n"
+        "xor.b32 y, %0, %2;\n"
+        "setp.ne.u32 q, z, 0;\n"
+        "setp.lt.and.s32 p, y, 0, !q;\n"
+        "@!p add.u32 %0, %0, %0;\n"
+        "@!p mad.lo.u32 %1, %1, 2, 1;\n"
+        "}\n"
+        : "+r"(a), "+r"(wa)
+        : "r"(b));
+    fin = 1u;
+  }
+#else
+  fin = ((int32_t)(a ^ b) < 0 && ((a & ~b) & 0x40000000u) == 0u) ? 1u : 0u;
+  if (!fin) {
+    a = a + a;
+    wa = wa + wa + 1u;
+  }
+#endif
+  flip = a & 0x80000000u;
+  c.x1 = a & 0x7FFFFFFFu;
+  c.w = wa;
+  const int j0 = 33 - (int)sh;
+  return fin ? j0 - (j0 != 0 ? 1 : 0) : j0; /* j0 = 0: the state is final as it stands */
+}
+/* one coded bit: P = Counter::p << 16 of a 1 */
+template <bool kNeedShift = true>
+W3_HD int w3_coder_step(w3_coder &c, uint32_t bit, uint32_t P, uint32_t &flip, uint32_t &x1p, uint32_t &x2p,
+                        uint32_t ones = 0xFFFFFFFFu) {
+  const uint32_t m = w3_umulhi(c.w, P);
+  x1p = bit ? c.x1 : c.x1 + m + 1u;   /* 1 takes the lower sub-range (:46-47) */
+  const uint32_t nw = bit ? m : c.w - m - 1u;
+  x2p = x1p + nw;
+  return w3_coder_renorm<kNeedShift>(c, x1p, nw, flip, ones);
+}
+
 /* ---- Counter — src/models/counter.rs ------------------------------------- */
 /* Counter::p (:13-18) with c0,c1 <= 65534 */
 W3_HD uint32_t w3_counter_p(uint32_t c0, uint32_t c1) {

@@ -92,12 +92,14 @@ __device__ __noinline__ bool w3_wait_gt(uint32_t flag_a, uint32_t v, uint32_t ab
 /* ------------------------------------------------------------------------ */
 /* encode                                                                   */
 
+#ifndef W3_OUT_RING
 #define W3_OUT_RING 16u /* groups of 32 coder steps in flight between coder and writer */
+#endif
 
 struct w3_enc_team {
   uint32_t stats[W3_NCTX];            /* c0 | c1 << 16 */
   uint32_t ring[W3_ENC_RING][32];     /* model -> coder: (p << 16) | bit per coded bit */
-  uint2 oring[W3_OUT_RING][32];       /* coder -> writer: x1 before renorm, s | k << 8 per step */
+  uint2 oring[W3_OUT_RING][32];       /* coder -> writer: the bounds (x1, x2) after narrowing, per step */
   uint32_t prod_done;                 /* groups written by the model warp */
   uint32_t cons_done;                 /* groups consumed by the coder warp */
   uint32_t out_done;                  /* groups of steps published by the coder warp */
@@ -216,22 +218,52 @@ w3_encode_blocks_team(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t
   }
 
   if (warp == 0) {
-    /* ---- coder warp: the x1/x2 chain of ac.encode (main.rs:107) and nothing
-     * else.  Per step it reads one ring entry and publishes (x1 before renorm,
-     * s, k); turning those into output bits is the writer warp's job.  The
-     * steady state is 32 steps of straight-line code. */
-    uint32_t x1 = 0, x2 = 0xFFFFFFFFu;
+    /* ---- coder warp: the range chain of ac.encode (main.rs:107) and nothing
+     * else, carried as (x1, width) with one clz per step (w3_coder_step).  A
+     * lone warp pays 2.3-2.7 cycles per INSTRUCTION, on or off the chain
+     * (profiles/r01_microbench1_coder_steps.txt), so per step it reads one ring
+     * entry and publishes the two bounds as they are after narrowing, nothing
+     * more: how many bits that emits and how many it leaves pending is worked
+     * out by the writer warp, 32 steps per instruction.  The steady state is 32
+     * steps of straight-line code. */
+    w3_coder cw = w3_coder_new();
+    uint32_t ones;
+    /* 0xFFFFFFFF, read back from shared memory: anything ptxas can see through it folds into a
+     * constant again, and then spends a move per use to get it into a register */
+    w3_sts(w3_saddr(&tm->final_x2), 0xFFFFFFFFu);
+    ones = w3_lds(w3_saddr(&tm->final_x2));
+    auto coder_step = [&](uint32_t vj) -> uint2 {
+      uint32_t flip, x1p, x2p;
+      (void)w3_coder_step<false>(cw, vj & 1u, vj & 0xFFFF0000u, flip, x1p, x2p, ones);
+      return make_uint2(x1p, x2p);
+    };
     uint32_t ready = 0, room = W3_OUT_RING;
+#ifdef W3_DEBUG
+    long long dbg_wait_model = 0, dbg_wait_writer = 0, dbg_n_model = 0, dbg_n_writer = 0;
+    const long long dbg_c0 = clock64();
+#endif
     const uint32_t ring_u = w3_saddr(&tm->ring[0][0]);
     const uint32_t oring_u = w3_saddr(&tm->oring[0][0]);
     for (uint32_t g = 0; g < n_words; g++) {
       if (ready <= g) {
+#ifdef W3_DEBUG
+        const long long dbg_w0 = clock64();
+#endif
         if (!w3_wait_gt(prod_a, g, abort_a)) return;
         ready = w3_lds(prod_a);
+#ifdef W3_DEBUG
+        dbg_wait_model += clock64() - dbg_w0; dbg_n_model++;
+#endif
       }
       if (g >= room) {
+#ifdef W3_DEBUG
+        const long long dbg_w0 = clock64();
+#endif
         if (!w3_wait_gt(wr_a, g - W3_OUT_RING, abort_a)) return;
         room = w3_lds(wr_a) + W3_OUT_RING;
+#ifdef W3_DEBUG
+        dbg_wait_writer += clock64() - dbg_w0; dbg_n_writer++;
+#endif
       }
       const uint32_t ga = ring_u + (g & (W3_ENC_RING - 1u)) * 128u;
       const uint32_t oa = oring_u + (g & (W3_OUT_RING - 1u)) * 256u;
@@ -243,31 +275,23 @@ w3_encode_blocks_team(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t
           const uint32_t vj = v0;
           v0 = v1;
           if (j + 2u < 32u) v1 = w3_lds(ga + (j + 2u) * 4u);
-          w3_ac_narrow(x1, x2, vj & 1u, vj & 0xFFFF0000u);
-          const uint32_t pre = x1;
-          int s, k;
-          w3_ac_renorm(x1, x2, s, k);
-          w3_sts64(oa + j * 8u, make_uint2(pre, (uint32_t)s | ((uint32_t)k << 8)));
+          w3_sts64(oa + j * 8u, coder_step(vj));
         }
       } else {
-        for (uint32_t j = 0; j < 32u; j++) {
-          uint32_t pre = 0;
-          int s = 0, k = 0;
-          if (j < left) {
-            const uint32_t vj = w3_lds(ga + j * 4u);
-            w3_ac_narrow(x1, x2, vj & 1u, vj & 0xFFFF0000u);
-            pre = x1;
-            w3_ac_renorm(x1, x2, s, k);
-          }
-          w3_sts64(oa + j * 8u, make_uint2(pre, (uint32_t)s | ((uint32_t)k << 8)));
-        }
+        for (uint32_t j = 0; j < 32u; j++) /* past the end: bounds that emit nothing */
+          w3_sts64(oa + j * 8u, j < left ? coder_step(w3_lds(ga + j * 4u)) : make_uint2(0u, 0xFFFFFFFFu));
       }
       w3_sts(cons_a, g + 1u);
-      if (g + 1u == n_words) w3_sts(w3_saddr(&tm->final_x2), x2);
+      if (g + 1u == n_words) w3_sts(w3_saddr(&tm->final_x2), cw.x1 + cw.w);
+#ifndef W3_UNSAFE_NO_CODER_FENCE /* experiment only */
       __threadfence_block();
+#endif
       w3_sts(out_a, g + 1u);
     }
-    if (n_words == 0) w3_sts(w3_saddr(&tm->final_x2), x2);
+    if (n_words == 0) w3_sts(w3_saddr(&tm->final_x2), cw.x1 + cw.w);
+#ifdef W3_DEBUG
+    if (blk == 0 && lane == 0 && n_words) printf("[w3] coder: %.1f cycles/bit; waits for the model warp %lld (%.1f cycles/bit), for the writer warp %lld (%.1f cycles/bit)\n", (double)(clock64() - dbg_c0) / (n_words * 32.0), dbg_n_model, (double)dbg_wait_model / (n_words * 32.0), dbg_n_writer, (double)dbg_wait_writer / (n_words * 32.0));
+#endif
     return;
   }
 
@@ -297,7 +321,16 @@ w3_encode_blocks_team(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t
     const uint2 e = w3_lds64(oring_l + (g & (W3_OUT_RING - 1u)) * 256u);
     __syncwarp();
     if (lane == 0) w3_sts(wr_a, g + 1u); /* entries are in registers now */
-    const uint32_t s_l = e.y & 0xFFu, k_l = e.y >> 8;
+    /* e = this step's bounds after narrowing: s = their common prefix (emitted
+     * plainly), k = the E3 shifts that follow (arithmetic_coder.rs:51-62) */
+    uint32_t s_l, k_l;
+    {
+      uint32_t b1 = e.x, b2 = e.y;
+      int si, ki;
+      w3_ac_renorm(b1, b2, si, ki);
+      s_l = (uint32_t)si;
+      k_l = (uint32_t)ki;
+    }
     /* inclusive prefix sum of k over the group */
     uint32_t pk = k_l;
 #pragma unroll
@@ -307,6 +340,9 @@ w3_encode_blocks_team(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t
     }
     const uint32_t total_k = __shfl_sync(FULL, pk, 31);
     uint32_t hm = __ballot_sync(FULL, s_l != 0u);
+#ifdef W3_UNSAFE_NO_WRITER /* experiment only: is the writer warp the encoder's limit? */
+    hm = 0;
+#endif
     /* pending bits before the group's first emitting step come from wr.rev;
      * `base` = exclusive prefix of k at the previous emitting step */
     uint32_t base = 0;
@@ -376,6 +412,7 @@ struct w3_dec_team {
   uint32_t abort_flag;
   uint32_t fed;                             /* stream words staged so far (feeder -> decoder) */
   uint32_t cons;                            /* decoder's current stream word (decoder -> feeder); ~0 = done */
+  uint32_t ones_word;                       /* 0xFFFFFFFF, read back into a register */
   uint32_t done[8];                         /* per alignment a: positions = a mod 8 up to done[a] have their
                                                predecessor's counter update in place and may be predicted */
 #ifdef W3_DEBUG
@@ -558,7 +595,7 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
   if (threadIdx.x < 8) tm->done[threadIdx.x] = threadIdx.x;
   if (threadIdx.x < W3_BIT_BARS)
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(w3_saddr(&tm->bars[threadIdx.x])) : "memory");
-  if (threadIdx.x == 0) { tm->pub = make_uint2(0u, 0u); tm->abort_flag = 0; tm->fed = 0; tm->cons = 0; }
+  if (threadIdx.x == 0) { tm->ones_word = 0xFFFFFFFFu; tm->pub = make_uint2(0u, 0u); tm->abort_flag = 0; tm->fed = 0; tm->cons = 0; }
   __syncthreads();
 
   const uint32_t blk = blockIdx.x;
@@ -812,6 +849,10 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
   uint32_t t = 0;
 
   const uint32_t lane0 = lane == 0u ? 1u : 0u; /* one arrival per bit */
+#ifdef W3_DEC_WIDTH_CODER
+  w3_coder cw = w3_coder_new();
+  const uint32_t ones = w3_lds(W3_TM_A(ones_word)); /* 0xFFFFFFFF that ptxas cannot fold (w3_coder_renorm) */
+#endif
   auto attempt = [&]() {
     /* candidates of the bit to decode after this attempt: bit t+1 (indexed by
      * bits t-1.., chosen by bit t) if this attempt decodes, bit t (indexed by
@@ -822,9 +863,20 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
     const uint2 pair_n = w3_lds64(pair_a);
 #endif
     const uint2 sw = w3_lds64(sring_a + ((bp >> 5) & (W3_SRING - 1u)) * 8u);
+#ifdef W3_DEC_WIDTH_CODER
+    /* x <= x1 + m (arithmetic_coder.rs:81-82); x >= x1 always */
+    const uint32_t bit = (x - cw.x1) <= xmid ? 1u : 0u;
+    uint32_t nx1 = cw.x1, nw = cw.w; /* not ok: a normalised range renormalises to itself */
+    if (ok && bit) nw = xmid;
+    if (ok && !bit) {
+      nx1 = cw.x1 + xmid + 1u;
+      nw = cw.w - xmid - 1u;
+    }
+#else
     const uint32_t bit = x <= xmid ? 1u : 0u; /* arithmetic_coder.rs:82 */
     if (ok && bit) x2 = xmid;
     if (ok && !bit) x1 = xmid + 1u;
+#endif
     if (ok) {
       rlo = __funnelshift_r(rlo, rhist, 1);
       rhist = __funnelshift_r(rhist, bit, 1);
@@ -847,18 +899,28 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
 #ifndef W3_FETCH_EARLY
     const uint2 pair_n = w3_lds64(pair_a);
 #endif
-    int s, k;
-    const int nsh = w3_ac_renorm(x1, x2, s, k);
     /* x <<= nsh with stream bits shifted in; of the E3 flips only the last one
      * survives the shifts (arithmetic_coder.rs:98-102): flip iff k > 0 */
     const uint32_t fresh = __funnelshift_l(sw.y, sw.x, bp & 31u);
+#ifdef W3_DEC_WIDTH_CODER
+    uint32_t flip;
+    const int nsh = w3_coder_renorm(cw, nx1, nw, flip, ones);
+    x = __funnelshift_l(fresh, x, (uint32_t)nsh) ^ flip;
+#else
+    int s, k;
+    const int nsh = w3_ac_renorm(x1, x2, s, k);
     x = __funnelshift_l(fresh, x, (uint32_t)nsh) ^ ((0u - (uint32_t)k) & 0x80000000u);
+#endif
     bp += (uint32_t)nsh;
     /* the newest decoded bit picks the entry; its own tag says whether it is
      * the published candidate of bit t (a speculator lane whose fixed lookup
      * declined publishes a non-matching tag first, the real entry later) */
     const uint32_t sel = ((int32_t)rhist < 0) ? pair_n.y : pair_n.x;
+#ifdef W3_DEC_WIDTH_CODER
+    xmid = __umulhi(cw.w, sel & 0xFFFF0000u); /* the split point minus x1 */
+#else
     xmid = x1 + __umulhi(x2 - x1, sel & 0xFFFF0000u);
+#endif
     ok = (((sel ^ (t + 1u)) & 0xFFFFu) == 0u) ? 1u : 0u;
   };
   /* make sure the staged stream reaches `words` beyond the current position */
