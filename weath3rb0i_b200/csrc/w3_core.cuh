@@ -222,6 +222,22 @@ W3_HD int w3_coder_step(w3_coder &c, uint32_t bit, uint32_t P, uint32_t &flip, u
   return w3_coder_renorm<kNeedShift>(c, x1p, nw, flip, ones);
 }
 
+/* w3_ac_renorm with the caller's all-ones register (see w3_coder_renorm): x2's
+ * new low bits come in through one funnel shift */
+W3_HD int w3_ac_renorm_ones(uint32_t &x1, uint32_t &x2, int &s, int &k, uint32_t ones) {
+  s = w3_clz32_nz(x1 ^ x2);
+  uint32_t h = (((~x1 | x2) << 1) | 1u) << s;
+  k = w3_clz32_nz(h);
+  int n = s + k;
+  x1 = (x1 << n) & 0x7FFFFFFFu;
+#if defined(__CUDA_ARCH__)
+  x2 = __funnelshift_l(ones, x2, (uint32_t)n) | 0x80000000u;
+#else
+  x2 = (x2 << n) | ~(ones << n) | 0x80000000u;
+#endif
+  return n;
+}
+
 /* ---- Counter — src/models/counter.rs ------------------------------------- */
 /* Counter::p (:13-18) with c0,c1 <= 65534 */
 W3_HD uint32_t w3_counter_p(uint32_t c0, uint32_t c1) {

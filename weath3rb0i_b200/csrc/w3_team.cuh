@@ -386,7 +386,8 @@ w3_encode_blocks_team(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t
 /* decode                                                                   */
 
 #define W3_SRING 128u /* stream words staged in shared memory for the decoder */
-#define W3_BIT_BARS 32u
+#define W3_BIT_BARS W3_CAND_RING /* one per candidate slot, at the slot's stride: the decoder derives both addresses from one offset */
+#define W3_BAR_STRIDE (W3_NGUESS * 4u)
 #define W3_NGUESS (1u << W3_SPEC_D)
 
 #define W3_THI_ROW 264u
@@ -407,7 +408,8 @@ struct w3_dec_team {
   uint32_t cand[W3_CAND_RING][W3_NGUESS];   /* (Counter::p << 16) | tag for every guess of the last 6 bits;
                                                tag = (pos + 1) & 0xFFFF marks the entry as position pos's */
   uint2 sring[W3_SRING];                    /* entry i = big-endian stream words (i, i+1) */
-  unsigned long long bars[W3_BIT_BARS];     /* mbarrier per decoded bit (mod W3_BIT_BARS): the decoder arrives, speculators sleep on it */
+  unsigned long long bars[W3_BIT_BARS][W3_BAR_STRIDE / 8u]; /* [s][0]: mbarrier of the decoded bits k with (k + 1) mod 16 = s —
+                                               the decoder arrives, speculators sleep on it */
   uint2 pub;                                /* x = last 32 decoded bits, newest highest; y = bits decoded (one STS.64) */
   uint32_t abort_flag;
   uint32_t fed;                             /* stream words staged so far (feeder -> decoder) */
@@ -470,37 +472,34 @@ __device__ __forceinline__ w3_fix w3_rank_fixed_sw(uint32_t khi, uint32_t a, uin
   const uint32_t ta = thi_a + (a * W3_THI_ROW + base) * 4u;
   /* slot of context (rank << 3) | a is a * 256 + rank (w3_dec_slot) */
   const uint32_t pa = probs_a + (a * 256u + base) * 4u;
-  uint32_t b[W3_FIX_THR], Pc[W3_FIX_THR + 1];
-  Pc[0] = w3_lds(pa);
-#pragma unroll
-  for (int i = 0; i < W3_FIX_THR; i++) {
-    b[i] = 0xFFFFFFFFu; /* "greater than any key": thresholds past the cell's */
-    Pc[i + 1] = 0u;
-    if (cnt > (uint32_t)i) {
-      b[i] = w3_ldc32(ta + (uint32_t)i * 4u);
-      Pc[i + 1] = w3_lds(pa + (uint32_t)(i + 1) * 4u);
-    }
-  }
-  /* thresholds ascend: the compares read 1..1 0..0, the answer is Pc[their sum].
-   * Everything below is a tree, not a chain (this warp issues in order: a
-   * serial count of six would delay the publishing store by ~50 cycles). */
+  /* A probability word carries its own rank in the low byte (W3_PROB_RANK), so
+   * selecting the probability selects the rank: no count of the compares.
+   * Loads and compares beyond the cell's count are predicated off; what they
+   * would have produced is never looked at. */
+  uint32_t Pc[W3_FIX_THR + 1];
   bool gt[W3_FIX_THR];
+  Pc[0] = w3_lds(pa);
   bool bad = cnt > (uint32_t)W3_FIX_THR;
 #pragma unroll
   for (int i = 0; i < W3_FIX_THR; i++) {
-    gt[i] = khi > b[i];
-    bad |= khi == b[i];
+    gt[i] = false;
+    if (cnt > (uint32_t)i) {
+      const uint32_t bi = w3_ldc32(ta + (uint32_t)i * 4u);
+      Pc[i + 1] = w3_lds(pa + (uint32_t)(i + 1) * 4u);
+      gt[i] = khi > bi;
+      bad |= khi == bi;
+    }
   }
-  static_assert(W3_FIX_THR == 6, "the select/sum trees below are written for six thresholds");
+  /* thresholds ascend: the compares read 1..1 0..0, the answer is Pc[their
+   * count] — picked by a tree, not a chain */
+  static_assert(W3_FIX_THR == 6, "the select tree below is written for six thresholds");
   const uint32_t Pa = gt[1] ? Pc[2] : (gt[0] ? Pc[1] : Pc[0]);
   const uint32_t Pb = gt[3] ? Pc[4] : Pc[3];
   const uint32_t Pd = gt[5] ? Pc[6] : Pc[5];
   const uint32_t P = gt[4] ? Pd : (gt[2] ? Pb : Pa);
-  const uint32_t r = base + (((gt[0] ? 1u : 0u) + (gt[1] ? 1u : 0u) + (gt[2] ? 1u : 0u)) +
-                             ((gt[3] ? 1u : 0u) + (gt[4] ? 1u : 0u) + (gt[5] ? 1u : 0u)));
   w3_fix f;
-  f.r = r;
-  f.P = P;
+  f.r = P & 0xFFu;
+  f.P = P & 0xFFFF0000u;
   f.e = e;
   f.bad = bad;
   return f;
@@ -522,15 +521,17 @@ __device__ __forceinline__ void w3_known_absorb(w3_known &kn) {
   kn.known = kn.pv.y;
 }
 /* Sleep until the decoder has decoded `need` bits, then read what it published.
- * The decoder arrives on an mbarrier per bit (bars[bit & 31], one arrival per
+ * The decoder arrives on an mbarrier per bit (bars[(bit + 1) & 15], one arrival per
  * phase), a speculator waits for the phase of bit need-1 with try_wait: the
  * hardware parks the warp instead of having it spin.  That matters more than
  * the wait's own latency: spinning speculators took issue slots and
  * shared-memory wavefronts from the working ones and from the decoder (16
  * spinning warps doubled every lookup's duration; nanosleep in a spin loop wakes
- * too late).  No speculator ever lags the decoder by 32 bits — the decoder
- * needs every speculator's candidates within W3_SPEC_WARPS bits — so the phase
- * parity (bit index / 32, mod 2) is unambiguous.
+ * too late).  A speculator never waits for a bit 16 or more behind the decoder:
+ * it waits for bit pos-6 while the decoder cannot pass bit pos-1 without its
+ * candidates, and for bit pos while the decoder cannot pass bit pos+15 without
+ * the candidates this warp computes next (W3_SPEC_WARPS <= 16) — so the phase
+ * parity (bit index / 16, mod 2) is unambiguous.
  * Returns 0, or bit 31 set if the wait gave up (the caller's `late`). */
 #define W3_WAIT_LIMIT (1u << 20)
 __device__ __forceinline__ uint32_t w3_bits_wait(w3_known &kn, uint32_t need, uint32_t bars_a, uint32_t pub_a) {
@@ -552,7 +553,7 @@ __device__ __forceinline__ uint32_t w3_bits_wait(w3_known &kn, uint32_t need, ui
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(got)
-        : "r"(bars_a + (k & (W3_BIT_BARS - 1u)) * 8u), "r"((k / W3_BIT_BARS) & 1u), "n"(W3_WAIT_LIMIT)
+        : "r"(bars_a + ((k + 1u) & (W3_BIT_BARS - 1u)) * W3_BAR_STRIDE), "r"((k / W3_BIT_BARS) & 1u), "n"(W3_WAIT_LIMIT)
         : "memory");
   }
   kn.pv = w3_lds64(pub_a);
@@ -588,13 +589,13 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
     if (threadIdx.x == 0) st->max_bits = tab->max_bits;
   }
   for (uint32_t i = threadIdx.x; i < W3_NCTX + 8u; i += blockDim.x) {
-    tm->probs[i] = 0x80000000u; /* Counter::new: p = 32768 */
+    tm->probs[i] = 0x80000000u | (i & 0xFFu); /* Counter::new: p = 32768; low byte = the slot's rank (W3_PROB_RANK) */
     if (i < W3_NCTX) tm->counts[i] = 0u;
   }
   for (uint32_t i = threadIdx.x; i < W3_CAND_RING * W3_NGUESS; i += blockDim.x) (&tm->cand[0][0])[i] = 0u;
   if (threadIdx.x < 8) tm->done[threadIdx.x] = threadIdx.x;
   if (threadIdx.x < W3_BIT_BARS)
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(w3_saddr(&tm->bars[threadIdx.x])) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(w3_saddr(&tm->bars[threadIdx.x][0])) : "memory");
   if (threadIdx.x == 0) { tm->ones_word = 0xFFFFFFFFu; tm->pub = make_uint2(0u, 0u); tm->abort_flag = 0; tm->fed = 0; tm->cons = 0; }
   __syncthreads();
 
@@ -764,7 +765,7 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
         for (uint32_t i = 0; i < W3_GPL; i++) {
           if (f[i].bad) f[i].r = rank_slow(kb | ((uint64_t)ghi[i] << 32), pos, f[i].e);
           if (pos == 0u) f[i].r = W3_CTX0_RANKED >> W3_ALIGN_BITS;
-          f[i].P = w3_lds(probs_a + w3_dec_slot((f[i].r << W3_ALIGN_BITS) | a) * 4u);
+          f[i].P = w3_lds(probs_a + w3_dec_slot((f[i].r << W3_ALIGN_BITS) | a) * 4u) & 0xFFFF0000u;
           w3_sts(slot_a + i * 128u, f[i].P | tag);
         }
       }
@@ -805,7 +806,7 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
           if (W3_GPL == 1u || (hq >> 5) == i) { nv = nvi; np = npi; sq = sqi; }
         }
         w3_sts(counts_a + sq, nv);
-        w3_sts(probs_a + sq, np);
+        w3_sts(probs_a + sq, np | ((sq >> 2) & 0xFFu)); /* the slot's rank rides along (W3_PROB_RANK) */
         __threadfence_block();
         w3_sts(done_a + a * 4u, pos + 8u);
       }
@@ -844,52 +845,48 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
                          candidate index (its top bits) and, bit-reversed, the output */
   uint32_t rlo = 0;   /* the 32 bits before those (output words complete mid-trip) */
   bool dead = false;
-  uint32_t xmid = 0; /* split point for bit t (lerp, arithmetic_coder.rs:81); valid iff ok */
+  uint32_t xmid = 0; /* split point of bit t minus x1 (lerp, arithmetic_coder.rs:81); valid iff ok */
   uint32_t ok = 0;
   uint32_t t = 0;
 
+  /* Every instruction of this lone warp costs 2-3 cycles, on or off the dependent
+   * chain (profiles/r01_microbench1_coder_steps_v2.txt), so the attempt is written
+   * for instruction count: the split point is kept as an offset from x1 (no
+   * 64-bit addend for the multiply), the candidate address of a failed attempt
+   * is simply the previous one, the bit's mbarrier lives at the stride of the
+   * candidate slots so one offset serves both, x2's fill bits come through a
+   * funnel shift from a register of ones that ptxas cannot fold. */
   const uint32_t lane0 = lane == 0u ? 1u : 0u; /* one arrival per bit */
-#ifdef W3_DEC_WIDTH_CODER
-  w3_coder cw = w3_coder_new();
-  const uint32_t ones = w3_lds(W3_TM_A(ones_word)); /* 0xFFFFFFFF that ptxas cannot fold (w3_coder_renorm) */
-#endif
+  const uint32_t ones = w3_lds(W3_TM_A(ones_word));
+  uint32_t pair_a = cand_a; /* position 0, no history */
   auto attempt = [&]() {
-    /* candidates of the bit to decode after this attempt: bit t+1 (indexed by
-     * bits t-1.., chosen by bit t) if this attempt decodes, bit t (indexed by
-     * bits t-2.., chosen by bit t-1) if not */
-    const uint32_t idx = (ok ? rhist : (rhist << 1)) >> (33u - W3_SPEC_D);
-    const uint32_t pair_a = cand_a + ((t + ok) & (W3_CAND_RING - 1u)) * (W3_NGUESS * 4u) + idx * 8u;
+    /* ok: the attempt decodes bit t, and next needs the candidates of bit t+1
+     * (slot (t+1) mod 16, indexed by bits t-1.., chosen by bit t); not ok: it
+     * needs those of bit t again — the pair it fetched last time */
+    const uint32_t so = ((t + 1u) * W3_BAR_STRIDE) & ((W3_CAND_RING - 1u) * W3_BAR_STRIDE);
+    const uint32_t na = cand_a + so + (rhist >> (33u - W3_SPEC_D)) * 8u;
+    pair_a = ok ? na : pair_a;
 #ifdef W3_FETCH_EARLY
     const uint2 pair_n = w3_lds64(pair_a);
 #endif
     const uint2 sw = w3_lds64(sring_a + ((bp >> 5) & (W3_SRING - 1u)) * 8u);
-#ifdef W3_DEC_WIDTH_CODER
     /* x <= x1 + m (arithmetic_coder.rs:81-82); x >= x1 always */
-    const uint32_t bit = (x - cw.x1) <= xmid ? 1u : 0u;
-    uint32_t nx1 = cw.x1, nw = cw.w; /* not ok: a normalised range renormalises to itself */
-    if (ok && bit) nw = xmid;
-    if (ok && !bit) {
-      nx1 = cw.x1 + xmid + 1u;
-      nw = cw.w - xmid - 1u;
-    }
-#else
-    const uint32_t bit = x <= xmid ? 1u : 0u; /* arithmetic_coder.rs:82 */
-    if (ok && bit) x2 = xmid;
-    if (ok && !bit) x1 = xmid + 1u;
-#endif
+    const uint32_t bit = (x - x1) <= xmid ? 1u : 0u;
+    if (ok && bit) x2 = x1 + xmid;
+    if (ok && !bit) x1 = x1 + xmid + 1u;
     if (ok) {
       rlo = __funnelshift_r(rlo, rhist, 1);
       rhist = __funnelshift_r(rhist, bit, 1);
+      t += 1u;
     }
-    t += ok;
     w3_sts64(pub_a, make_uint2(rhist, t));
-    /* wake whoever waits for bit t-1 (release: after the word above) */
+    /* wake whoever waits for the bit just decoded (release: after the word above) */
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "setp.ne.u32 p, %1, 0;\n"
         "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n"
-        "}\n" ::"r"(bars_a + ((t - 1u) & (W3_BIT_BARS - 1u)) * 8u), "r"(ok & lane0)
+        "}\n" ::"r"(bars_a + so), "r"(ok & lane0)
         : "memory");
 #ifdef W3_DEBUG
     w3_sts(W3_TM_A(dbg_stamp) + (t & 63u) * 4u, (uint32_t)clock64());
@@ -901,26 +898,16 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
 #endif
     /* x <<= nsh with stream bits shifted in; of the E3 flips only the last one
      * survives the shifts (arithmetic_coder.rs:98-102): flip iff k > 0 */
-    const uint32_t fresh = __funnelshift_l(sw.y, sw.x, bp & 31u);
-#ifdef W3_DEC_WIDTH_CODER
-    uint32_t flip;
-    const int nsh = w3_coder_renorm(cw, nx1, nw, flip, ones);
-    x = __funnelshift_l(fresh, x, (uint32_t)nsh) ^ flip;
-#else
+    const uint32_t fresh = __funnelshift_l(sw.y, sw.x, bp);
     int s, k;
-    const int nsh = w3_ac_renorm(x1, x2, s, k);
+    const int nsh = w3_ac_renorm_ones(x1, x2, s, k, ones);
     x = __funnelshift_l(fresh, x, (uint32_t)nsh) ^ ((0u - (uint32_t)k) & 0x80000000u);
-#endif
     bp += (uint32_t)nsh;
     /* the newest decoded bit picks the entry; its own tag says whether it is
      * the published candidate of bit t (a speculator lane whose fixed lookup
      * declined publishes a non-matching tag first, the real entry later) */
     const uint32_t sel = ((int32_t)rhist < 0) ? pair_n.y : pair_n.x;
-#ifdef W3_DEC_WIDTH_CODER
-    xmid = __umulhi(cw.w, sel & 0xFFFF0000u); /* the split point minus x1 */
-#else
-    xmid = x1 + __umulhi(x2 - x1, sel & 0xFFFF0000u);
-#endif
+    xmid = __umulhi(x2 - x1, sel & 0xFFFF0000u); /* the split point minus x1 */
     ok = (((sel ^ (t + 1u)) & 0xFFFFu) == 0u) ? 1u : 0u;
   };
   /* make sure the staged stream reaches `words` beyond the current position */
