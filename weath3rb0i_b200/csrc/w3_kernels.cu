@@ -589,14 +589,18 @@ static inline int w3_pick_warps(uint32_t n_blocks, int sm_count) {
   return w;
 }
 
-/* W3_MODE=warp|team overrides the choice; by default the team kernels run while
- * every block's CTA can be resident at once (encode: 3 CTAs of ~68 KiB shared
- * memory per SM; decode: 1 CTA of ~170 KiB) */
-static inline bool w3_use_team(uint32_t n_blocks, int sm_count, uint32_t ctas_per_sm) {
+/* W3_MODE=warp|team overrides the choice.  By default the team kernels (one CTA
+ * per block: 3 resident per SM for encode, 1 for decode) run in as many waves as
+ * it takes while that beats stacking 8 one-warp blocks on an SM — measured on
+ * 1 GiB (profiles/r01_modes_1gib.txt): encode 840-1120 MB/s against 294-1075
+ * up to 1024 blocks (warp kernels: 1586 at 4096 blocks), decode 260-277 against
+ * 100-247 up to 683 blocks (warp kernels: 371 against 297 at 1024).
+ * `max_per_sm` = blocks per SM up to which the team kernel is chosen. */
+static inline bool w3_use_team(uint32_t n_blocks, int sm_count, uint32_t max_per_sm) {
   const char *m = getenv("W3_MODE");
   if (m && !strcmp(m, "warp")) return false;
   if (m && !strcmp(m, "team")) return true;
-  return n_blocks <= ctas_per_sm * (uint32_t)sm_count;
+  return n_blocks <= max_per_sm * (uint32_t)sm_count;
 }
 
 extern "C" {
@@ -631,7 +635,7 @@ cudaError_t w3_launch_encode(const uint8_t *d_in, uint64_t n_total, uint32_t blo
                              uint32_t *d_lens, uint32_t *d_overflow, const w3_hashtab *d_tab,
                              int sm_count, cudaStream_t s) {
   if (!n_blocks) return cudaSuccess;
-  if (w3_use_team(n_blocks, sm_count, 3u)) {
+  if (w3_use_team(n_blocks, sm_count, 8u)) {
     w3_encode_blocks_team<<<n_blocks, W3_ENC_TEAM_THREADS, sizeof(w3_smem_tab) + sizeof(w3_enc_team), s>>>(
         d_in, n_total, block_size, n_blocks, d_scratch, stride, d_lens, d_overflow, d_tab);
     return cudaGetLastError();
@@ -665,7 +669,7 @@ cudaError_t w3_launch_decode(const uint8_t *d_comp, const uint64_t *d_offsets, u
                              uint32_t *d_err, const w3_hashtab *d_tab, int sm_count,
                              cudaStream_t s) {
   if (!n_blocks) return cudaSuccess;
-  if (w3_use_team(n_blocks, sm_count, 1u)) {
+  if (w3_use_team(n_blocks, sm_count, 5u)) {
     w3_decode_blocks_team<<<n_blocks, W3_DEC_TEAM_THREADS,
                             sizeof(w3_dec_tab) + sizeof(w3_dec_team), s>>>(
         d_comp, d_offsets, n_blocks, block_size, n_total, d_out, d_err, d_tab);

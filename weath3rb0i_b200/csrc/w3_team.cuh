@@ -465,10 +465,17 @@ __device__ __forceinline__ uint32_t w3_ldc32(uint32_t a) {
  * one probability and nothing else.  Fewer wavefronts matter: the speculators
  * kept the shared-memory pipe 44% busy, 39% of that bank-conflict replays
  * (profiles/r01_ncu_decode_team_v8.txt), which is latency for the decoder. */
+#ifndef W3_DEC_FIX
+#define W3_DEC_FIX 6 /* thresholds the speculators' fixed-latency lookup covers (<= W3_FIX_THR: the table rows' padding) */
+#endif
 __device__ __forceinline__ w3_fix w3_rank_fixed_sw(uint32_t khi, uint32_t a, uint32_t sw,
                                                    uint32_t thi_a, uint32_t cell2_a, uint32_t probs_a) {
   const uint32_t e = w3_ldc16(cell2_a + (a * W3_NCELL2 + sw) * 2u);
+#ifdef W3_UNSAFE_NO_THR /* experiment only: how much do the speculators' loads cost the decoder? */
+  const uint32_t base = e & 0xFFu, cnt = 0;
+#else
   const uint32_t base = e & 0xFFu, cnt = e >> 8;
+#endif
   const uint32_t ta = thi_a + (a * W3_THI_ROW + base) * 4u;
   /* slot of context (rank << 3) | a is a * 256 + rank (w3_dec_slot) */
   const uint32_t pa = probs_a + (a * 256u + base) * 4u;
@@ -476,27 +483,44 @@ __device__ __forceinline__ w3_fix w3_rank_fixed_sw(uint32_t khi, uint32_t a, uin
    * selecting the probability selects the rank: no count of the compares.
    * Loads and compares beyond the cell's count are predicated off; what they
    * would have produced is never looked at. */
-  uint32_t Pc[W3_FIX_THR + 1];
-  bool gt[W3_FIX_THR];
+  uint32_t Pc[W3_DEC_FIX + 1];
+  bool gt[W3_DEC_FIX];
   Pc[0] = w3_lds(pa);
-  bool bad = cnt > (uint32_t)W3_FIX_THR;
+  bool bad = cnt > (uint32_t)W3_DEC_FIX;
 #pragma unroll
-  for (int i = 0; i < W3_FIX_THR; i++) {
+  for (int i = 0; i < W3_DEC_FIX; i++) {
     gt[i] = false;
     if (cnt > (uint32_t)i) {
       const uint32_t bi = w3_ldc32(ta + (uint32_t)i * 4u);
       Pc[i + 1] = w3_lds(pa + (uint32_t)(i + 1) * 4u);
+#ifndef W3_P_AFTER_COMPARE
+      /* an opaque use: left alone the compiler predicates this load on the compare
+       * below (it is only needed if that holds), which puts a third shared-memory
+       * round trip on the path to the publishing store */
+      asm volatile("" : "+r"(Pc[i + 1]));
+#endif
       gt[i] = khi > bi;
       bad |= khi == bi;
     }
   }
   /* thresholds ascend: the compares read 1..1 0..0, the answer is Pc[their
    * count] — picked by a tree, not a chain */
-  static_assert(W3_FIX_THR == 6, "the select tree below is written for six thresholds");
+#if W3_DEC_FIX == 6
   const uint32_t Pa = gt[1] ? Pc[2] : (gt[0] ? Pc[1] : Pc[0]);
   const uint32_t Pb = gt[3] ? Pc[4] : Pc[3];
   const uint32_t Pd = gt[5] ? Pc[6] : Pc[5];
   const uint32_t P = gt[4] ? Pd : (gt[2] ? Pb : Pa);
+#elif W3_DEC_FIX == 4
+  const uint32_t Pa = gt[1] ? Pc[2] : (gt[0] ? Pc[1] : Pc[0]);
+  const uint32_t Pb = gt[3] ? Pc[4] : Pc[3];
+  const uint32_t P = gt[2] ? Pb : Pa;
+#elif W3_DEC_FIX == 3
+  const uint32_t Pa = gt[0] ? Pc[1] : Pc[0];
+  const uint32_t Pb = gt[2] ? Pc[3] : Pc[2];
+  const uint32_t P = gt[1] ? Pb : Pa;
+#else
+#error "write the select tree for this W3_DEC_FIX"
+#endif
   w3_fix f;
   f.r = P & 0xFFu;
   f.P = P & 0xFFFF0000u;
@@ -880,6 +904,9 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
       t += 1u;
     }
     w3_sts64(pub_a, make_uint2(rhist, t));
+#if !defined(W3_FETCH_EARLY) && defined(W3_FETCH_BEFORE_ARRIVE)
+    const uint2 pair_n = w3_lds64(pair_a);
+#endif
     /* wake whoever waits for the bit just decoded (release: after the word above) */
     asm volatile(
         "{\n"
@@ -891,9 +918,14 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
 #ifdef W3_DEBUG
     w3_sts(W3_TM_A(dbg_stamp) + (t & 63u) * 4u, (uint32_t)clock64());
 #endif
-    /* fetched as late as the renormalisation's latency hides: every cycle here
-     * is a cycle more for the speculators */
-#ifndef W3_FETCH_EARLY
+    /* The candidates of the next bit are fetched as late as the renormalisation's
+     * latency hides: the speculators publish just in time (their latency is about
+     * five attempts), so an earlier fetch — at the attempt's start, or ahead of
+     * the arrival, which delays it by a dozen cycles in the memory pipe's queue —
+     * makes the attempt shorter (105 cycles instead of 118) and 16 % of the
+     * attempts fail: 123 instead of 121 cycles per bit
+     * (profiles/r01_decode_team_experiments.txt). */
+#if !defined(W3_FETCH_EARLY) && !defined(W3_FETCH_BEFORE_ARRIVE)
     const uint2 pair_n = w3_lds64(pair_a);
 #endif
     /* x <<= nsh with stream bits shifted in; of the E3 flips only the last one
