@@ -36,6 +36,13 @@
  * every wait is bounded and trips an abort flag instead of hanging.  Rare paths
  * are out of line so that the steady-state loops are straight-line code: a
  * branch costs a lone warp 20-40 cycles (profiles/r01_microbench5_*).
+ *
+ * Build-time switches (scripts/variants.sh builds A/B libraries with them; what
+ * each measured is in profiles/r01_{encode,decode}_team_experiments.txt):
+ *   W3_SPEC_WARPS 8|16, W3_DEC_FIX 3|4|6, W3_ATTEMPTS_PER_TRIP, W3_OUT_RING  sizes
+ *   W3_FETCH_EARLY, W3_FETCH_BEFORE_ARRIVE, W3_P_AFTER_COMPARE                 schedule variants
+ *   W3_STATS, W3_DEBUG                                                           counters / clock64 probes + printf
+ *   W3_UNSAFE_*  take a part of the work out (wrong output!) to bound its cost; never shipped
  */
 #pragma once
 
