@@ -75,7 +75,15 @@ uint32_t hs_counter_p(uint32_t c0, uint32_t c1) { return w3_counter_p(c0, c1); }
 uint64_t hs_counter_p_sweep(uint32_t c0_lo, uint32_t c0_hi, uint32_t step) {
   uint64_t bad = 0;
   for (uint32_t c0 = c0_lo; c0 < c0_hi; c0 += step)
-    for (uint32_t c1 = 0; c1 <= 65534; c1++) bad += w3_counter_p(c0, c1) != w3_counter_p_u64(c0, c1);
+    for (uint32_t c1 = 0; c1 <= 65534; c1++) {
+      bad += w3_counter_p(c0, c1) != w3_counter_p_u64(c0, c1);
+      const uint32_t slot = c0 | (c1 << 16);
+      uint32_t p0, p1;
+      w3_counter_p_both(slot, p0, p1);
+      const uint32_t n0 = w3_counter_update(slot, 0u), n1 = w3_counter_update(slot, 1u);
+      bad += p0 != w3_counter_p_u64(n0 & 0xFFFFu, n0 >> 16);
+      bad += p1 != w3_counter_p_u64(n1 & 0xFFFFu, n1 >> 16);
+    }
   return bad;
 }
 uint32_t hs_counter_update(uint32_t slot, uint32_t bit) { return w3_counter_update(slot, bit); }

@@ -274,6 +274,42 @@ W3_HD uint32_t w3_counter_update(uint32_t slot, uint32_t bit) {
   return v;
 }
 
+/* 1/d for the float estimates of Counter::p; d >= 2: no denormal or overflow case */
+W3_HD float w3_rcp_of(uint32_t d) {
+#if defined(__CUDA_ARCH__)
+  float rcp;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"((float)d));
+  return rcp;
+#else
+  return 1.0f / (float)d;
+#endif
+}
+/* Counter::p after Counter::update with a 0 and with a 1, from the counter as it
+ * stands (slot = c0 | c1 << 16): what the decode speculators prepare for every
+ * guessed context.  Unless the update halves (counter.rs:22-25; then the general
+ * functions run) both new states share the total d = c0 + c1 + 3, hence one
+ * reciprocal; and since the float estimate is within 0.03 of the quotient, its
+ * floor is within one of the true one: a single correction each way.  The
+ * device self-test checks every counter state against the u64 statement. */
+W3_HD void w3_counter_p_both(uint32_t slot, uint32_t &p0, uint32_t &p1) {
+  const uint32_t c0 = slot & 0xFFFFu, c1 = slot >> 16;
+  if (c0 >= 0xFFFEu || c1 >= 0xFFFEu) { /* an update would reach 65535 and halve */
+    const uint32_t n0 = w3_counter_update(slot, 0u), n1 = w3_counter_update(slot, 1u);
+    p0 = w3_counter_p(n0 & 0xFFFFu, n0 >> 16);
+    p1 = w3_counter_p(n1 & 0xFFFFu, n1 >> 16);
+    return;
+  }
+  const uint32_t d = c0 + c1 + 3u;
+  const float r17 = w3_rcp_of(d) * 131072.0f; /* exact scaling */
+  const uint32_t a0 = c1 + 1u, a1 = c1 + 2u;
+  uint32_t q0 = (uint32_t)((float)a0 * r17), q1 = (uint32_t)((float)a1 * r17);
+  const int32_t rem0 = (int32_t)((a0 << 17) - q0 * d), rem1 = (int32_t)((a1 << 17) - q1 * d);
+  q0 = q0 - ((uint32_t)rem0 >> 31) + (rem0 >= (int32_t)d ? 1u : 0u);
+  q1 = q1 - ((uint32_t)rem1 >> 31) + (rem1 >= (int32_t)d ? 1u : 0u);
+  p0 = (q0 >> 1) + (q0 & 1u);
+  p1 = (q1 >> 1) + (q1 & 1u);
+}
+
 /* ---- ACHistory::hash, literal — src/history/ac_history.rs:28-88 ----------- */
 struct w3_hash_result {
   uint32_t hash; /* state >> (32 - idx) (:45), 0 when idx == 0 */

@@ -516,8 +516,16 @@ __global__ void w3_k_hash_array(const uint64_t *bits, const uint32_t *pos, uint3
 __global__ void w3_k_counter_p_check(unsigned long long *mismatches) {
   const uint32_t c0 = blockIdx.x; /* 0..65534 */
   unsigned long long bad = 0;
-  for (uint32_t c1 = threadIdx.x; c1 <= 65534u; c1 += blockDim.x)
+  for (uint32_t c1 = threadIdx.x; c1 <= 65534u; c1 += blockDim.x) {
     bad += w3_counter_p(c0, c1) != w3_counter_p_u64(c0, c1);
+    /* the speculators' pair form: both updates of this state */
+    const uint32_t slot = c0 | (c1 << 16);
+    uint32_t p0, p1;
+    w3_counter_p_both(slot, p0, p1);
+    const uint32_t n0 = w3_counter_update(slot, 0u), n1 = w3_counter_update(slot, 1u);
+    bad += p0 != w3_counter_p_u64(n0 & 0xFFFFu, n0 >> 16);
+    bad += p1 != w3_counter_p_u64(n1 & 0xFFFFu, n1 >> 16);
+  }
   if (bad) atomicAdd(mismatches, bad);
 }
 

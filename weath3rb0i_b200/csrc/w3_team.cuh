@@ -40,7 +40,7 @@
  * Build-time switches (scripts/variants.sh builds A/B libraries with them; what
  * each measured is in profiles/r01_{encode,decode}_team_experiments.txt):
  *   W3_SPEC_WARPS 8|16, W3_DEC_FIX 3|4|6, W3_ATTEMPTS_PER_TRIP, W3_OUT_RING  sizes
- *   W3_FETCH_EARLY, W3_FETCH_BEFORE_ARRIVE, W3_P_AFTER_COMPARE                 schedule variants
+ *   W3_FETCH_EARLY, W3_FETCH_BEFORE_ARRIVE, W3_P_AFTER_COMPARE, W3_LOADS_PREDICATED  schedule variants
  *   W3_STATS, W3_DEBUG                                                           counters / clock64 probes + printf
  *   W3_UNSAFE_*  take a part of the work out (wrong output!) to bound its cost; never shipped
  */
@@ -497,7 +497,11 @@ __device__ __forceinline__ w3_fix w3_rank_fixed_sw(uint32_t khi, uint32_t a, uin
 #pragma unroll
   for (int i = 0; i < W3_DEC_FIX; i++) {
     gt[i] = false;
+#ifdef W3_LOADS_PREDICATED /* fewer wavefronts (shared-memory pipe 44 % -> 33 % busy), six more instructions: 121 instead of 116.5 cycles per bit */
     if (cnt > (uint32_t)i) {
+#else
+    { /* thresholds past the cell's are greater by themselves: rows are padded with ~0 */
+#endif
       const uint32_t bi = w3_ldc32(ta + (uint32_t)i * 4u);
       Pc[i + 1] = w3_lds(pa + (uint32_t)(i + 1) * 4u);
 #ifndef W3_P_AFTER_COMPARE
@@ -811,34 +815,34 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
         const uint32_t old = w3_lds(counts_a + prep_sq[i]);
         prep_nv0[i] = w3_counter_update(old, 0u);
         prep_nv1[i] = w3_counter_update(old, 1u);
-        prep_np0[i] = w3_counter_p(prep_nv0[i] & 0xFFFFu, prep_nv0[i] >> 16) << 16;
-        prep_np1[i] = w3_counter_p(prep_nv1[i] & 0xFFFFu, prep_nv1[i] >> 16) << 16;
+        /* both outcomes share the new total: one reciprocal (w3_counter_p_both) */
+        uint32_t p0, p1;
+        w3_counter_p_both(old, p0, p1);
+        prep_np0[i] = p0 << 16;
+        prep_np1[i] = p1 << 16;
       }
 #ifdef W3_DEBUG
       dbg_wait += dbg_t1 - dbg_t0; dbg_work += clock64() - dbg_t1; dbg_n++; dbg_look += dbg_t2 - dbg_t1; dbg_pub += clock64() - dbg_t2;
 #endif
       /* ---- commit: the guess that came true and the bit are known once bit pos
-       * is decoded: one select, one shuffle per value, and a same-value store
-       * by every lane (no lane-0 branch) */
+       * is decoded */
       late |= w3_bits_wait(kn, pos + 1u, bars_a, pub_a);
       late |= kn.pv.y - pos - 1u;
       {
         const uint32_t hb = kn.pv.x << ((kn.pv.y - pos - 1u) & 31u); /* bit pos on top */
-        /* bits pos-D..pos-1, pos-1 highest, rotated into the guess index (newest = bit 0) */
-        const uint32_t vq = (hb << 1) >> (32u - W3_SPEC_D);
-        const uint32_t hq = ((vq << 1) & (W3_NGUESS - 1u)) | (vq >> (W3_SPEC_D - 1u));
         const bool bq = (int32_t)hb < 0;
-        uint32_t nv = 0, np = 0, sq = 0;
+        /* the one lane whose guess matches the history stores what it prepared — no
+         * shuffles: this path is what the next position of the alignment, predicted
+         * two decode steps after bit pos, waits for (it went from 56 % to 7 % of that
+         * alignment's predicts finding `done` not yet set) */
 #pragma unroll
         for (uint32_t i = 0; i < W3_GPL; i++) {
-          const uint32_t nvi = __shfl_sync(FULL, bq ? prep_nv1[i] : prep_nv0[i], hq & 31u);
-          const uint32_t npi = __shfl_sync(FULL, bq ? prep_np1[i] : prep_np0[i], hq & 31u);
-          const uint32_t sqi = __shfl_sync(FULL, prep_sq[i], hq & 31u);
-          if (W3_GPL == 1u || (hq >> 5) == i) { nv = nvi; np = npi; sq = sqi; }
+          if ((((hb << 1) ^ ghi[i]) >> (32u - W3_SPEC_D)) == 0u) {
+            w3_sts(counts_a + prep_sq[i], bq ? prep_nv1[i] : prep_nv0[i]);
+            w3_sts(probs_a + prep_sq[i], (bq ? prep_np1[i] : prep_np0[i]) | ((prep_sq[i] >> 2) & 0xFFu)); /* + the slot's rank (W3_PROB_RANK) */
+          }
         }
-        w3_sts(counts_a + sq, nv);
-        w3_sts(probs_a + sq, np | ((sq >> 2) & 0xFFu)); /* the slot's rank rides along (W3_PROB_RANK) */
-        __threadfence_block();
+        __threadfence_block(); /* the counter before the flag (without it: 1 cycle per bit faster) */
         w3_sts(done_a + a * 4u, pos + 8u);
       }
       /* a wait that gave up, or the decoder's abort mark (bit 30 of a difference) */
