@@ -880,8 +880,8 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
                          candidate index (its top bits) and, bit-reversed, the output */
   uint32_t rlo = 0;   /* the 32 bits before those (output words complete mid-trip) */
   bool dead = false;
-  uint32_t xmid = 0; /* split point of bit t minus x1 (lerp, arithmetic_coder.rs:81); valid iff ok */
-  uint32_t ok = 0;
+  uint32_t xmid = 0; /* split point of bit t minus x1 (lerp, arithmetic_coder.rs:81); valid iff miss == 0 */
+  uint32_t miss = 1; /* tag mismatch bits of the candidate xmid was built from: the attempt decodes iff 0 */
   uint32_t t = 0;
 
   /* Every instruction of this lone warp costs 2-3 cycles, on or off the dependent
@@ -891,7 +891,7 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
    * is simply the previous one, the bit's mbarrier lives at the stride of the
    * candidate slots so one offset serves both, x2's fill bits come through a
    * funnel shift from a register of ones that ptxas cannot fold. */
-  const uint32_t lane0 = lane == 0u ? 1u : 0u; /* one arrival per bit */
+  const uint32_t not_lane0 = lane == 0u ? 0u : 1u; /* one arrival per bit: lane 0's */
   const uint32_t ones = w3_lds(W3_TM_A(ones_word));
   uint32_t pair_a = cand_a; /* position 0, no history */
   auto attempt = [&]() {
@@ -900,6 +900,7 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
      * needs those of bit t again — the pair it fetched last time */
     const uint32_t so = ((t + 1u) * W3_BAR_STRIDE) & ((W3_CAND_RING - 1u) * W3_BAR_STRIDE);
     const uint32_t na = cand_a + so + (rhist >> (33u - W3_SPEC_D)) * 8u;
+    const bool ok = miss == 0u;
     pair_a = ok ? na : pair_a;
 #ifdef W3_FETCH_EARLY
     const uint2 pair_n = w3_lds64(pair_a);
@@ -922,9 +923,9 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "setp.ne.u32 p, %1, 0;\n"
+        "setp.eq.u32 p, %1, 0;\n"
         "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n"
-        "}\n" ::"r"(bars_a + so), "r"(ok & lane0)
+        "}\n" ::"r"(bars_a + so), "r"(miss | not_lane0)
         : "memory");
 #ifdef W3_DEBUG
     w3_sts(W3_TM_A(dbg_stamp) + (t & 63u) * 4u, (uint32_t)clock64());
@@ -951,7 +952,7 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
      * declined publishes a non-matching tag first, the real entry later) */
     const uint32_t sel = ((int32_t)rhist < 0) ? pair_n.y : pair_n.x;
     xmid = __umulhi(x2 - x1, sel & 0xFFFF0000u); /* the split point minus x1 */
-    ok = (((sel ^ (t + 1u)) & 0xFFFFu) == 0u) ? 1u : 0u;
+    miss = (sel ^ (t + 1u)) & 0xFFFFu;
   };
   /* make sure the staged stream reaches `words` beyond the current position */
   auto need_stream = [&](uint32_t words) -> bool {
