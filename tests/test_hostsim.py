@@ -63,6 +63,9 @@ def test_hash_table_other_model(libs):
 
 
 def test_counter_p_estimate_is_exact(libs):
+    """w3_counter_p (float estimate + integer fix-up) and w3_counter_p_both (both updates of a state
+    from one reciprocal, one correction each way) against the u64 statement of counter.rs:13-18;
+    the device runs the same sweep over all 65535^2 states (tests/test_gpu_parity.py)."""
     lib = libs.hostsim.lib
     assert lib.hs_counter_p_sweep(0, 2048, 1) == 0
     assert lib.hs_counter_p_sweep(2048, 65535, 61) == 0
