@@ -42,6 +42,7 @@
  *   W3_SPEC_WARPS 8|16, W3_DEC_FIX 3|4|6, W3_ATTEMPTS_PER_TRIP, W3_OUT_RING  sizes
  *   W3_FETCH_EARLY, W3_FETCH_BEFORE_ARRIVE, W3_P_AFTER_COMPARE, W3_LOADS_PREDICATED  schedule variants
  *   W3_STATS, W3_DEBUG                                                           counters / clock64 probes + printf
+ *                      (a W3_STATS build runs up to 5 % faster or slower than the plain one: compare like builds)
  *   W3_UNSAFE_*  take a part of the work out (wrong output!) to bound its cost; never shipped
  */
 #pragma once
@@ -934,9 +935,10 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
      * latency hides: the speculators publish just in time (their latency is about
      * five attempts), so an earlier fetch — at the attempt's start, or ahead of
      * the arrival, which delays it by a dozen cycles in the memory pipe's queue —
-     * makes the attempt shorter (105 cycles instead of 118) and 16 % of the
-     * attempts fail: 123 instead of 121 cycles per bit
-     * (profiles/r01_decode_team_experiments.txt). */
+     * shortens the attempt by a dozen cycles and makes more attempts fail.
+     * Measured every time the speculators got faster: late has stayed ahead
+     * (108.6 against 109.6 cycles per bit at the last count,
+     * profiles/r01_decode_team_experiments.txt). */
 #if !defined(W3_FETCH_EARLY) && !defined(W3_FETCH_BEFORE_ARRIVE)
     const uint2 pair_n = w3_lds64(pair_a);
 #endif
