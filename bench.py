@@ -330,6 +330,16 @@ def run_b200(args):
             "gpu_launches": 4 * K,
             "clocks": clocks,
         }
+        # SURVEY.md §8(d), figure 2: the same 8 sectors per input byte against the box's MEASURED
+        # random 32-byte-sector gather rate (w3_probe_sector_gather, outside the timed region)
+        try:
+            rate = ctx.sector_gather_rate(4 << 30)
+            sectors = n * 8 / (dom_ms / 1e3)
+            line["gather_roofline"] = {"kernel": dom, "achieved": round(sectors / 1e9, 3), "peak": round(rate / 1e9, 3),
+                                       "unit": "G sectors/s", "frac": round(sectors / rate, 6),
+                                       "peak_source": "measured here: one independent random 32-B sector per load over a 4 GiB buffer"}
+        except Exception as e:  # a measurement aid: never fails the bench
+            line["gather_roofline"] = {"error": str(e)[:120]}
         if world == 1 and not args.no_cpu:
             threads = host_threads()
             nb_cpu = max(1, min(n_blocks, threads))

@@ -121,6 +121,13 @@ int w3_selftest_achash(w3_ctx *ctx, const uint64_t *bits, const uint32_t *pos, s
 /* Counter::p (src/models/counter.rs:13-18): all 65535^2 count pairs, float estimate
  * vs the u64 statement, on the device; *mismatches must come back 0 */
 int w3_selftest_counter_p(w3_ctx *ctx, uint64_t *mismatches);
+
+/* Measurement support (bench.py): random 32-byte-sector loads per second of the
+ * context's first device from a scratch buffer of `buffer_bytes` (>= 4 GiB to
+ * stay out of L2) — the denominator of the gather roofline SURVEY.md §8(d)
+ * defines for this path (8 context lookups = 8 sectors per input byte).  No
+ * counterpart in the reference. */
+int w3_probe_sector_gather(w3_ctx *ctx, size_t buffer_bytes, double *sectors_per_second);
 /* the coder with caller-supplied probabilities — the harness of
  * src/entropy_coding/arithmetic_coder_tests.rs:8-42; `in` is read MSB-first */
 int w3_selftest_ac_encode(w3_ctx *ctx, const uint8_t *in, size_t n_in, const uint16_t *probs,

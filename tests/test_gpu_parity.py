@@ -76,6 +76,13 @@ def test_golden_hashes_device(ctx):
     assert ctx.achash(bits, pos) == [w for _, _, w in g["achash"]]
 
 
+def test_sector_gather_probe_is_plausible(ctx):
+    """bench.py's gather-roofline denominator: between a tenth of and the hard ceiling of
+    HBM bandwidth / 32 B (6498.7e9 / 32 = 203 G sectors/s)."""
+    rate = ctx.sector_gather_rate(1 << 30)
+    assert 5e9 < rate < 260e9, rate
+
+
 def test_counter_p_exhaustive_on_device(ctx):
     assert ctx.counter_p_mismatches() == 0
 

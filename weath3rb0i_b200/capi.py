@@ -21,7 +21,7 @@ SYMBOLS = (
     "w3_ctx_set_model", "w3_ctx_get_model", "w3_train_model",
     "w3_compress", "w3_decompress", "w3_decompressed_size",
     "w3_encode_device", "w3_pack_device", "w3_decode_device",
-    "w3_selftest_achash", "w3_selftest_counter_p", "w3_selftest_ac_encode", "w3_selftest_ac_decode",
+    "w3_selftest_achash", "w3_selftest_counter_p", "w3_probe_sector_gather", "w3_selftest_ac_encode", "w3_selftest_ac_decode",
     "w3_strerror", "w3_last_cuda_error", "w3_version",
 )
 
@@ -67,6 +67,7 @@ def load():
     lib.w3_decode_device.argtypes = [vp, C.c_int, vp, vp, sz, sz, sz, vp, vp, vp]
     lib.w3_selftest_achash.argtypes = [vp, vp, vp, sz, vp]
     lib.w3_selftest_counter_p.argtypes = [vp, C.POINTER(C.c_uint64)]
+    lib.w3_probe_sector_gather.argtypes = [vp, sz, C.POINTER(C.c_double)]
     lib.w3_selftest_ac_encode.argtypes = [vp, u8p, sz, vp, sz, u8p, sz, C.POINTER(sz)]
     lib.w3_selftest_ac_decode.argtypes = [vp, u8p, sz, vp, sz, u8p, sz]
     for f in ("w3_strerror", "w3_last_cuda_error", "w3_version"):
@@ -201,6 +202,12 @@ class Context:
         m = C.c_uint64(1)
         check(self.lib.w3_selftest_counter_p(self.handle, C.byref(m)))
         return m.value
+
+    def sector_gather_rate(self, buffer_bytes: int = 4 << 30) -> float:
+        """Random 32-byte-sector loads per second of the first device (gather roofline denominator)."""
+        r = C.c_double(0.0)
+        check(self.lib.w3_probe_sector_gather(self.handle, buffer_bytes, C.byref(r)))
+        return r.value
 
     def ac_encode_probs(self, data: bytes, probs) -> bytes:
         n = len(probs)

@@ -524,6 +524,39 @@ int w3_selftest_counter_p(w3_ctx *ctx, uint64_t *mismatches) {
   return W3_OK;
 }
 
+int w3_probe_sector_gather(w3_ctx *ctx, size_t buffer_bytes, double *sectors_per_second) {
+  if (!ctx || !sectors_per_second || buffer_bytes < (1u << 20)) return W3_E_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  w3_dev &d = ctx->d[0];
+  CK(cudaSetDevice(d.ordinal));
+  void *buf = nullptr;
+  unsigned long long *sink = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int rc = W3_OK;
+  float ms = 0.f;
+  const uint64_t n_sectors = std::min<uint64_t>(buffer_bytes / 32, 0xFFFFFFFFull);
+  const uint32_t blocks = (uint32_t)d.sm_count * 32u, per_thread = 64u;
+  auto fin = [&](cudaError_t e) { if (e != cudaSuccess && rc == W3_OK) rc = cuda_fail(e, "w3_probe_sector_gather"); };
+  fin(cudaMalloc(&buf, n_sectors * 32));
+  if (rc == W3_OK) fin(cudaMalloc((void **)&sink, 8));
+  if (rc == W3_OK) fin(cudaMemsetAsync(buf, 0x5A, n_sectors * 32, d.stream));
+  if (rc == W3_OK) fin(cudaMemsetAsync(sink, 0, 8, d.stream));
+  if (rc == W3_OK) fin(cudaEventCreate(&e0));
+  if (rc == W3_OK) fin(cudaEventCreate(&e1));
+  if (rc == W3_OK) fin(w3_launch_gather_probe(buf, n_sectors, blocks, per_thread, sink, d.stream)); /* warm-up */
+  if (rc == W3_OK) fin(cudaEventRecord(e0, d.stream));
+  for (int r = 0; r < 3 && rc == W3_OK; r++) fin(w3_launch_gather_probe(buf, n_sectors, blocks, per_thread, sink, d.stream));
+  if (rc == W3_OK) fin(cudaEventRecord(e1, d.stream));
+  if (rc == W3_OK) fin(cudaStreamSynchronize(d.stream));
+  if (rc == W3_OK) fin(cudaEventElapsedTime(&ms, e0, e1));
+  if (rc == W3_OK) *sectors_per_second = 3.0 * (double)blocks * 256.0 * per_thread / ((double)ms * 1e-3);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (sink) cudaFree(sink);
+  if (buf) cudaFree(buf);
+  return rc;
+}
+
 int w3_selftest_ac_encode(w3_ctx *ctx, const uint8_t *in, size_t n_in, const uint16_t *probs,
                           size_t n_probs, uint8_t *out, size_t cap, size_t *out_len) {
   if (!ctx || !in || !probs || !out || !out_len || n_in * 8 < n_probs || n_probs > 0x7FFFFFFF)

@@ -529,6 +529,23 @@ __global__ void w3_k_counter_p_check(unsigned long long *mismatches) {
   if (bad) atomicAdd(mismatches, bad);
 }
 
+/* Random 32-byte-sector gather probe: the denominator of the gather roofline
+ * (SURVEY.md §8(d)): every thread loads `per_thread` independent sectors at
+ * hashed indices of a buffer much larger than L2 and folds them into a sink. */
+__global__ void w3_k_gather_probe(const uint4 *__restrict__ buf, uint64_t n_sectors, uint32_t per_thread,
+                                  unsigned long long *sink) {
+  uint64_t x = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
+  uint32_t acc = 0;
+#pragma unroll 8 /* eight independent sectors in flight per thread */
+  for (uint32_t i = 0; i < per_thread; i++) {
+    x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32; /* independent of the loaded data: loads overlap */
+    const uint64_t sct = ((x >> 32) * (n_sectors & 0xFFFFFFFFull)) >> 32; /* < n_sectors <= 2^32 - 1 (capped by the caller) */
+    const uint4 a = __ldg(buf + 2 * sct), b = __ldg(buf + 2 * sct + 1);
+    acc ^= a.x ^ a.y ^ a.z ^ a.w ^ b.x ^ b.y ^ b.z ^ b.w;
+  }
+  if (acc == 0x12345677u) atomicAdd(sink, 1ull); /* keeps the loads alive */
+}
+
 /* the coder alone with caller-supplied probabilities (the reference's KAT
  * harness, arithmetic_coder_tests.rs:8-42), one thread.  Handles prob == 0 /
  * x1 == x2 (32 shifts), which the codec kernels never meet. */
@@ -702,6 +719,12 @@ cudaError_t w3_launch_hash_array(const uint64_t *d_bits, const uint32_t *d_pos, 
   w3_k_hash_array<<<64, 256, sizeof(w3_smem_tab), s>>>(d_bits, d_pos, n, d_out, d_tab);
   return cudaGetLastError();
 }
+cudaError_t w3_launch_gather_probe(const void *d_buf, uint64_t n_sectors, uint32_t blocks, uint32_t per_thread,
+                                   unsigned long long *d_sink, cudaStream_t s) {
+  w3_k_gather_probe<<<blocks, 256, 0, s>>>((const uint4 *)d_buf, n_sectors, per_thread, d_sink);
+  return cudaGetLastError();
+}
+
 cudaError_t w3_launch_counter_p_check(unsigned long long *d_mismatches, cudaStream_t s) {
   w3_k_counter_p_check<<<65535, 256, 0, s>>>(d_mismatches);
   return cudaGetLastError();

@@ -31,6 +31,8 @@ cudaError_t w3_launch_train(const uint8_t *d_in, uint64_t n, uint16_t *d_cnt, ui
 cudaError_t w3_launch_hash_array(const uint64_t *d_bits, const uint32_t *d_pos, uint32_t n,
                                  uint32_t *d_out, const struct w3_hashtab *d_tab, cudaStream_t s);
 cudaError_t w3_launch_counter_p_check(unsigned long long *d_mismatches, cudaStream_t s);
+cudaError_t w3_launch_gather_probe(const void *d_buf, uint64_t n_sectors, uint32_t blocks, uint32_t per_thread,
+                                   unsigned long long *d_sink, cudaStream_t s);
 cudaError_t w3_launch_ac_encode_probs(const uint8_t *d_in, const uint16_t *d_probs,
                                       uint32_t n_probs, uint8_t *d_out, uint32_t cap,
                                       uint32_t *d_out_len, cudaStream_t s);
