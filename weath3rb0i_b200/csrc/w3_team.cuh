@@ -999,7 +999,15 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
   if (blk == 0 && lane == 0) printf("[w3] A: %u bits, %.1f cycles/bit overall; %.1f cycles/attempt, %.3f attempts/bit\n", nbits, (double)(clock64() - dbg_a0) / nbits, (double)(clock64() - dbg_a0) / (16.0 * dbg_trips), 16.0 * dbg_trips / nbits);
 #endif
   w3_sts(cons_a, 0xFFFFFFFFu); /* releases the feeder */
-  if (dead) w3_sts64(pub_a, make_uint2(0u, W3_PUB_ABORT)); /* and, when giving up, the speculators */
+  if (dead) { /* giving up: release the speculators too */
+    w3_sts64(pub_a, make_uint2(0u, W3_PUB_ABORT));
+    __threadfence_block();
+    /* they sleep on mbarriers no decoded bit will complete any more: one arrival on
+     * each ends the phase they wait for; they wake, read the mark above and leave */
+    if (lane == 0)
+      for (uint32_t sl = 0; sl < W3_BIT_BARS; sl++)
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars_a + sl * W3_BAR_STRIDE) : "memory");
+  }
   if (lane == 0) {
     const uint32_t rem = n & 3u; /* bytes after the last whole word */
     const uint32_t hist = __brev(rhist); /* newest bit lowest */
