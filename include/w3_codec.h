@@ -31,6 +31,10 @@ extern "C" {
 #define W3_E_CUDA (-4)   /* CUDA error or no device; w3_last_cuda_error() has the text */
 #define W3_E_FORMAT (-5) /* container header or index is inconsistent / truncated */
 #define W3_E_TABLE (-6)  /* threshold-table self-check failed at context creation */
+#define W3_E_TOOBIG (-7) /* a single stream or block is larger than the kernels' 32-bit bit counters allow:
+                            one block <= 256 MiB, one stream < 512 MiB.  The reference streams a file of any
+                            length as ONE stream (src/main.rs:96, u64 length); files above the block limit
+                            must use the w3Bk container (which the reference cannot read) */
 
 /* flags for w3_compress */
 #define W3_F_LEGACY 1u /* one block, reference file format: "w30i" + u64 BE length + stream
@@ -49,6 +53,14 @@ typedef struct w3_ctx w3_ctx;
 int w3_ctx_create(const int *devices, int n_devices, w3_ctx **out);
 void w3_ctx_destroy(w3_ctx *ctx);
 int w3_ctx_device_count(const w3_ctx *ctx);
+
+/* Launch options of a context (no counterpart in the reference; tests and measurements use them
+ * to pin a kernel family instead of the launcher's choice by block count). */
+#define W3_OPT_KERNELS 1    /* 0 auto | 1 team: one CTA per block | 2 warp: one warp per block (round 1)
+                               | 3 many-block: teams sharing a CTA (encode), one lane per block (decode) */
+#define W3_OPT_ENC_TEAMS 2  /* blocks per CTA of the team encoder, 1..8; 0 auto */
+#define W3_OPT_LANE_WARPS 3 /* warps per CTA of the lane decoder, 1..8; 0 auto */
+int w3_ctx_set_option(w3_ctx *ctx, int option, int value);
 
 /* ---- the StationaryModel of the entropy hash -------------------------------
  * init_model() fixes StationaryModel::for_book1 (src/main.rs:151) and that is

@@ -35,8 +35,9 @@ def build_hostsim():
     d = os.path.join(ROOT, "tests", "hostsim")
     so = os.path.join(d, "libw3hostsim.so")
     core = os.path.join(ROOT, "weath3rb0i_b200", "csrc", "w3_core.cuh")
+    lane = os.path.join(ROOT, "weath3rb0i_b200", "csrc", "w3_lane.cuh")
     src = os.path.join(d, "w3_hostsim.cpp")
-    if not _newer(so, src, core):
+    if not _newer(so, src, core, lane):
         subprocess.check_call(
             ["g++", "-O2", "-std=c++17", "-Wall", "-shared", "-fPIC", "-o", so, src]
         )
@@ -180,6 +181,7 @@ class HostSim:
         h.hs_counter_p_sweep.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
         h.hs_compress_block.argtypes = [C.c_void_p, C.c_char_p, sz, C.c_void_p, sz, C.POINTER(sz)]
         h.hs_decompress_block.argtypes = [C.c_void_p, C.c_char_p, sz, C.c_void_p, sz]
+        h.hs_lane_decode_block.argtypes = [C.c_void_p, C.c_char_p, sz, C.c_uint, C.c_uint8, C.c_void_p, sz]
         self.lib = h
         self.table = (C.c_uint16 * 8)(*table)
         self.max_bits = max_bits
@@ -206,6 +208,12 @@ class HostSim:
     def decompress_block(self, stream: bytes, n_out: int) -> bytes:
         out = C.create_string_buffer(max(n_out, 1))
         self.lib.hs_decompress_block(self.tab, stream, len(stream), out, n_out)
+        return out.raw[:n_out]
+
+    def lane_decode_block(self, stream: bytes, n_out: int, misalign: int = 0, junk: int = 0xA5) -> bytes:
+        """w3_lane.cuh's per-lane decoder (what w3_decode_blocks_lane runs in every lane)."""
+        out = C.create_string_buffer(max(n_out, 1))
+        self.lib.hs_lane_decode_block(self.tab, stream, len(stream), misalign, junk, out, n_out)
         return out.raw[:n_out]
 
     def thresholds(self):

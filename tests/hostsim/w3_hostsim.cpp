@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../weath3rb0i_b200/csrc/w3_core.cuh"
+#include "../../weath3rb0i_b200/csrc/w3_lane.cuh"
 
 extern "C" {
 
@@ -205,6 +206,25 @@ int hs_decompress_block(const w3_hashtab *tab, const uint8_t *in, size_t n_in, u
     }
     out[i] = (uint8_t)byte;
   }
+  return 0;
+}
+
+/* the lane decoder (w3_lane.cuh: what every lane of w3_decode_blocks_lane executes), on a copy of
+ * the stream placed `misalign` bytes past a word boundary and followed by `junk` (what the next
+ * block's stream would be in a packed buffer) */
+int hs_lane_decode_block(const w3_hashtab *tab, const uint8_t *in, size_t n_in, unsigned misalign,
+                         uint8_t junk, uint8_t *out, size_t n_out) {
+  std::vector<w3_lane_tab> lt(1);
+  for (uint32_t i = 0; i < 8u * W3_LANE_ROW; i++) lt[0].thi[i] = w3_lane_tab_thi(tab, i);
+  for (uint32_t i = 0; i < 8u * W3_LANE_NCELL; i++) lt[0].cellb[i] = w3_lane_tab_cellb(tab, i);
+  std::vector<uint32_t> buf((n_in + 64) / 4 + 8, 0x01010101u * junk);
+  uint8_t *sp = reinterpret_cast<uint8_t *>(buf.data()) + 4 + (misalign & 3u);
+  memcpy(sp, in, n_in);
+  std::vector<uint32_t> cnt(W3_NCTX, 0u);
+  std::vector<uint32_t> dst((n_out + 3) / 4 + 1, 0u);
+  w3_lane_decode_block(sp, (uint32_t)n_in, (uint32_t)n_out, reinterpret_cast<uint8_t *>(dst.data()), cnt.data(),
+                       lt.data(), tab, 0xFFFFFFFFu);
+  memcpy(out, dst.data(), n_out);
   return 0;
 }
 

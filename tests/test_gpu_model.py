@@ -20,10 +20,11 @@ def ctx():
     c.close()
 
 
-@pytest.fixture(params=["team", "warp"], autouse=True)
-def kernel_mode(request, monkeypatch):
-    monkeypatch.setenv("W3_MODE", request.param)
-    return request.param
+@pytest.fixture(params=["team", "many", "warp"], autouse=True)
+def kernel_mode(request, ctx):
+    ctx.set_kernels(request.param)
+    yield request.param
+    ctx.set_kernels("auto")
 
 
 def _split_v2(blob):
@@ -42,7 +43,7 @@ def _split_v2(blob):
 
 
 def test_train_model_equals_stationary_new(ctx, libs, kernel_mode):
-    if kernel_mode == "warp":
+    if kernel_mode != "team":
         pytest.skip("training does not depend on the codec kernel family")
     rnd = random.Random(31)
     cases = [
@@ -82,7 +83,7 @@ def test_from_table_models_code_like_the_oracle(ctx, libs):
 
 
 def test_achash_follows_the_model(ctx, libs, kernel_mode):
-    if kernel_mode == "warp":
+    if kernel_mode != "team":
         pytest.skip("hash self-test does not depend on the codec kernel family")
     rnd = random.Random(3)
     bits = [rnd.getrandbits(64) for _ in range(20000)]

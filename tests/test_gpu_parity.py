@@ -20,12 +20,15 @@ def ctx():
     c.close()
 
 
-@pytest.fixture(params=["team", "warp"], autouse=True)
-def kernel_mode(request, monkeypatch):
-    """Every test runs against both kernel families: `team` (one CTA per block,
-    coder warp + model/speculator warps) and `warp` (one warp per block)."""
-    monkeypatch.setenv("W3_MODE", request.param)
-    return request.param
+@pytest.fixture(params=["team", "many", "warp"], autouse=True)
+def kernel_mode(request, ctx):
+    """Every test runs against every kernel family (W3_OPT_KERNELS): `team` (one CTA per
+    block: coder warp + model / speculator warps), `many` (the many-block regime: teams
+    sharing a CTA for encode, one lane per block for decode) and `warp` (round 1's one
+    warp per block)."""
+    ctx.set_kernels(request.param)
+    yield request.param
+    ctx.set_kernels("auto")
 
 
 def split_container(blob):
@@ -270,19 +273,19 @@ def test_256mib_round_trip_and_sampled_blocks(ctx, libs, kernel_mode):
     kernel family that produced it."""
     import ctypes as C
 
-    if kernel_mode == "warp":
+    if kernel_mode != "team":
         pytest.skip("run once, with the launcher's own choice of kernels")
     n, block = 256 << 20, 1 << 20
     buf = C.create_string_buffer(n)
     w3_corpus.generate_into(C.addressof(buf), n)
     data = buf.raw
-    import os
-    os.environ.pop("W3_MODE", None)  # auto: team encode, warp decode at this block count
+    ctx.set_kernels("auto")  # teams sharing CTAs for encode, one lane per block for decode at this block count
     blob = ctx.compress(data, block)
     _, _, streams = split_container(blob)
     assert len(streams) == 256
     for i in (0, 97, 148, 255):
         assert streams[i] == libs.oracle.compress_block(data[i * block : (i + 1) * block]), i
     assert ctx.decompress(blob) == data
-    os.environ["W3_MODE"] = "warp"
-    assert hashlib.sha256(ctx.compress(data, block)).digest() == hashlib.sha256(blob).digest()
+    for mode in ("team", "warp"):
+        ctx.set_kernels(mode)
+        assert hashlib.sha256(ctx.compress(data, block)).digest() == hashlib.sha256(blob).digest(), mode

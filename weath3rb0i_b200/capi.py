@@ -11,13 +11,15 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("W3_LIB") or os.path.join(HERE, "libw3codec.so")  # W3_LIB: another build of the same library
 
-W3_OK, W3_E_ARG, W3_E_CAP, W3_E_MAGIC, W3_E_CUDA, W3_E_FORMAT, W3_E_TABLE = 0, -1, -2, -3, -4, -5, -6
+W3_OK, W3_E_ARG, W3_E_CAP, W3_E_MAGIC, W3_E_CUDA, W3_E_FORMAT, W3_E_TABLE, W3_E_TOOBIG = 0, -1, -2, -3, -4, -5, -6, -7
+W3_OPT_KERNELS, W3_OPT_ENC_TEAMS, W3_OPT_LANE_WARPS = 1, 2, 3
+KERNELS = {"auto": 0, "team": 1, "warp": 2, "many": 3}
 W3_F_LEGACY = 1
 DEFAULT_BLOCK = 1 << 20
 
 # every symbol include/w3_codec.h declares
 SYMBOLS = (
-    "w3_ctx_create", "w3_ctx_destroy", "w3_ctx_device_count", "w3_compress_bound",
+    "w3_ctx_create", "w3_ctx_destroy", "w3_ctx_device_count", "w3_ctx_set_option", "w3_compress_bound",
     "w3_ctx_set_model", "w3_ctx_get_model", "w3_train_model",
     "w3_compress", "w3_decompress", "w3_decompressed_size",
     "w3_encode_device", "w3_pack_device", "w3_decode_device",
@@ -54,6 +56,7 @@ def load():
     lib.w3_ctx_destroy.argtypes = [vp]
     lib.w3_ctx_destroy.restype = None
     lib.w3_ctx_device_count.argtypes = [vp]
+    lib.w3_ctx_set_option.argtypes = [vp, C.c_int, C.c_int]
     lib.w3_ctx_set_model.argtypes = [vp, vp]
     lib.w3_ctx_get_model.argtypes = [vp, vp]
     lib.w3_train_model.argtypes = [vp, u8p, sz, vp]
@@ -118,6 +121,13 @@ class Context:
             self.handle = None
 
     __del__ = close
+
+    def set_option(self, option: int, value: int) -> None:
+        check(self.lib.w3_ctx_set_option(self.handle, option, value))
+
+    def set_kernels(self, name: str) -> None:
+        """Pin the kernel family: auto | team | warp | many (include/w3_codec.h, W3_OPT_KERNELS)."""
+        self.set_option(W3_OPT_KERNELS, KERNELS[name])
 
     # ---- the StationaryModel (stationary.rs:14-46) -------------------------
     def set_model(self, table) -> None:

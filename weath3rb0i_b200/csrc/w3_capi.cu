@@ -9,6 +9,7 @@
  * an assert there).  There is no CPU path: every block is coded by a kernel.
  */
 #include <cuda_runtime.h>
+#include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -22,12 +23,22 @@
 #include "w3_kernels.h"
 
 static thread_local char g_cuda_err[256] = "";
-static char g_cuda_err_any[256] = "";
+static char g_cuda_err_any[256] = ""; /* the last message of any thread: the per-device worker threads' */
+static std::mutex g_err_mu;
 
-static int cuda_fail(cudaError_t e, const char *what) {
-  snprintf(g_cuda_err, sizeof g_cuda_err, "%s: %s", what, cudaGetErrorString(e));
+/* records a message for w3_last_cuda_error(): in the calling thread and, for messages raised on
+ * a per-device worker thread, where the thread that made the API call finds it */
+static int fail_msg(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_cuda_err, sizeof g_cuda_err, fmt, ap);
+  va_end(ap);
+  std::lock_guard<std::mutex> lock(g_err_mu);
   snprintf(g_cuda_err_any, sizeof g_cuda_err_any, "%s", g_cuda_err);
-  return W3_E_CUDA;
+  return code;
+}
+static int cuda_fail(cudaError_t e, const char *what) {
+  return fail_msg(W3_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
 }
 #define CK(call)                                              \
   do {                                                        \
@@ -39,6 +50,8 @@ static const uint8_t MAGIC_LEGACY[4] = {'w', '3', '0', 'i'}; /* src/main.rs:14 *
 static const uint8_t MAGIC_BLOCKS[4] = {'w', '3', 'B', 'k'};
 static const size_t HDR_LEGACY = 12, HDR_BLOCKS = 24, HDR_MODEL = 16; /* v2 appends the 8 u16 BE probabilities */
 static const size_t MAX_BLOCK = (size_t)256 << 20;
+/* the kernels count stream bytes and bits in 32 bits: a stream is at most this long */
+static const uint64_t MAX_STREAM = ((uint64_t)1 << 29) - 4096;
 
 struct w3_buf {
   void *p = nullptr;
@@ -66,7 +79,7 @@ struct w3_dev {
   int ordinal = 0, sm_count = 148;
   cudaStream_t stream = nullptr;
   w3_hashtab *d_tab = nullptr;
-  w3_buf in, scratch, lens, offsets, packed, out;
+  w3_buf in, scratch, scratch2, lens, lens2, alt, offsets, packed, out;
   uint32_t *d_flag = nullptr;
 };
 
@@ -76,6 +89,7 @@ struct w3_ctx {
   int n = 0;
   w3_dev d[W3_MAX_DEVICES];
   uint16_t table[8]; /* the StationaryModel in force (init_model: for_book1, src/main.rs:151) */
+  w3_launch_opts opts = {0, 0, 0}; /* w3_ctx_set_option */
   std::mutex mu;     /* one host call at a time per context */
 };
 
@@ -91,9 +105,7 @@ static int dev_init(w3_dev &d, int ordinal) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, ordinal));
   if (prop.major < 10) {
-    snprintf(g_cuda_err, sizeof g_cuda_err, "device %d is sm_%d%d; this library is built for sm_100a only",
-             ordinal, prop.major, prop.minor);
-    return W3_E_CUDA;
+    return fail_msg(W3_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", ordinal, prop.major, prop.minor);
   }
   d.sm_count = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
@@ -106,6 +118,9 @@ static int dev_init(w3_dev &d, int ordinal) {
 /* (re)build the threshold tables of device d for a StationaryModel table */
 static int dev_build_table(w3_dev &d, const uint16_t *table) {
   CK(cudaSetDevice(d.ordinal));
+  /* the table is rebuilt in place: launches of the device-resident entry points still in flight
+   * on the caller's streams read it, so let the device drain first (a model switch is rare) */
+  CK(cudaDeviceSynchronize());
   std::vector<uint8_t> host(sizeof(w3_hashtab), 0);
   w3_hashtab *h = reinterpret_cast<w3_hashtab *>(host.data());
   for (int i = 0; i < 8; i++) h->table[i] = table[i];
@@ -133,7 +148,8 @@ static int ctx_set_model(w3_ctx *ctx, const uint16_t *table) {
 
 static void dev_release(w3_dev &d) {
   cudaSetDevice(d.ordinal);
-  d.in.release(); d.scratch.release(); d.lens.release(); d.offsets.release();
+  d.in.release(); d.scratch.release(); d.scratch2.release(); d.lens.release(); d.lens2.release();
+  d.alt.release(); d.offsets.release();
   d.packed.release(); d.out.release();
   if (d.d_tab) cudaFree(d.d_tab);
   if (d.d_flag) cudaFree(d.d_flag);
@@ -163,7 +179,14 @@ static void block_range(size_t n_blocks, int n_dev, int g, size_t &b0, size_t &b
 extern "C" {
 
 const char *w3_version(void) { return "w3-b200 0.1 (sm_100a)"; }
-const char *w3_last_cuda_error(void) { return g_cuda_err[0] ? g_cuda_err : g_cuda_err_any; }
+const char *w3_last_cuda_error(void) {
+  /* the calling thread's own message if it has one, else the last one any thread recorded (a
+   * context on several devices raises them on its per-device worker threads) */
+  static thread_local char out[256];
+  std::lock_guard<std::mutex> lock(g_err_mu);
+  snprintf(out, sizeof out, "%s", g_cuda_err_any[0] ? g_cuda_err_any : g_cuda_err);
+  return out;
+}
 const char *w3_strerror(int code) {
   switch (code) {
     case W3_OK: return "ok";
@@ -173,6 +196,7 @@ const char *w3_strerror(int code) {
     case W3_E_CUDA: return "CUDA error (see w3_last_cuda_error)";
     case W3_E_FORMAT: return "inconsistent or truncated block container";
     case W3_E_TABLE: return "entropy-hash threshold table failed its self-check";
+    case W3_E_TOOBIG: return "stream or block too large for this build (one stream < 512 MiB, one block <= 256 MiB)";
     default: return "unknown error";
   }
 }
@@ -183,7 +207,7 @@ int w3_ctx_create(const int *devices, int n_devices, w3_ctx **out) {
   int have = 0;
   cudaError_t e = cudaGetDeviceCount(&have);
   if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
-  if (have < 1) { snprintf(g_cuda_err, sizeof g_cuda_err, "no CUDA device"); return W3_E_CUDA; }
+  if (have < 1) return fail_msg(W3_E_CUDA, "no CUDA device");
   w3_ctx *ctx = new w3_ctx();
   for (int i = 0; i < n_devices; i++) {
     int ord = devices ? devices[i] : i;
@@ -213,8 +237,20 @@ int w3_ctx_set_model(w3_ctx *ctx, const uint16_t *table) {
 
 int w3_ctx_get_model(const w3_ctx *ctx, uint16_t *table) {
   if (!ctx || !table) return W3_E_ARG;
+  std::lock_guard<std::mutex> lock(const_cast<w3_ctx *>(ctx)->mu);
   memcpy(table, ctx->table, sizeof ctx->table);
   return W3_OK;
+}
+
+int w3_ctx_set_option(w3_ctx *ctx, int option, int value) {
+  if (!ctx || value < 0) return W3_E_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  switch (option) {
+    case W3_OPT_KERNELS: if (value > 3) return W3_E_ARG; ctx->opts.kernels = value; return W3_OK;
+    case W3_OPT_ENC_TEAMS: if (value > 8) return W3_E_ARG; ctx->opts.enc_teams = value; return W3_OK;
+    case W3_OPT_LANE_WARPS: if (value > 8) return W3_E_ARG; ctx->opts.lane_warps = value; return W3_OK;
+    default: return W3_E_ARG;
+  }
 }
 
 int w3_train_model(w3_ctx *ctx, const uint8_t *in, size_t n, uint16_t *table) {
@@ -253,11 +289,12 @@ int w3_encode_device(w3_ctx *ctx, int dev, const void *d_in, size_t n, size_t bl
   size_t nb = (n + block_size - 1) / block_size;
   if (!nb) return W3_OK;
   if (!d_in || !d_scratch || nb > 0xFFFFFFFFull) return W3_E_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu); /* no model switch (table rebuild) while this is being enqueued */
   w3_dev &d = ctx->d[dev];
   CK(cudaSetDevice(d.ordinal));
   CK(w3_launch_encode((const uint8_t *)d_in, n, (uint32_t)block_size, (uint32_t)nb,
                       (uint8_t *)d_scratch, stride, d_lens, d_overflow, d.d_tab, d.sm_count,
-                      (cudaStream_t)stream));
+                      &ctx->opts, (cudaStream_t)stream));
   return W3_OK;
 }
 
@@ -268,7 +305,7 @@ int w3_pack_device(w3_ctx *ctx, int dev, const void *d_scratch, size_t stride,
   if (n_blocks && (!d_scratch || !d_lens || !d_packed)) return W3_E_ARG;
   w3_dev &d = ctx->d[dev];
   CK(cudaSetDevice(d.ordinal));
-  CK(w3_launch_pack((const uint8_t *)d_scratch, stride, d_lens, (uint32_t)n_blocks, d_offsets,
+  CK(w3_launch_pack((const uint8_t *)d_scratch, stride, d_lens, (uint32_t)n_blocks, d_offsets, nullptr,
                     (uint8_t *)d_packed, (cudaStream_t)stream));
   return W3_OK;
 }
@@ -281,11 +318,12 @@ int w3_decode_device(w3_ctx *ctx, int dev, const void *d_comp, const uint64_t *d
   if (n_blocks != (n + block_size - 1) / block_size || n_blocks > 0xFFFFFFFFull) return W3_E_ARG;
   if (!n_blocks) return W3_OK;
   if (!d_comp || !d_offsets || !d_out) return W3_E_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
   w3_dev &d = ctx->d[dev];
   CK(cudaSetDevice(d.ordinal));
   CK(w3_launch_decode((const uint8_t *)d_comp, d_offsets, (uint32_t)n_blocks, (uint32_t)block_size,
                       n, (uint8_t *)d_out, d_err ? d_err : d.d_flag, d.d_tab, d.sm_count,
-                      (cudaStream_t)stream));
+                      &ctx->opts, (cudaStream_t)stream));
   return W3_OK;
 }
 
@@ -313,28 +351,51 @@ static int encode_part(w3_ctx *ctx, int g, const uint8_t *in, size_t n, size_t b
   if ((rc = d.lens.ensure(nb * 4)) != W3_OK) return rc;
   if ((rc = d.offsets.ensure((nb + 1) * 8)) != W3_OK) return rc;
   CK(cudaMemcpyAsync(d.in.p, in + off, bytes, cudaMemcpyHostToDevice, d.stream));
-  /* text codes to ~0.45 n; leave generous room and retry at the hard bound
-   * (17 n: p >= 2^-16 caps the cost of one bit at 16 + eps bits) on overflow */
+  /* text codes to ~0.45 n; leave generous room.  A stream that does not fit is not stored beyond
+   * its region but still measured (lens holds its full length: at most 17 n, since p >= 2^-16 caps
+   * the cost of a bit at 16 + eps bits), so only the blocks that overflowed are coded again, each
+   * into a region of exactly the size it asked for. */
   size_t stride = round_up(bs + (bs >> 3) + 64, 16);
-  for (int attempt = 0;; attempt++) {
-    if ((rc = d.scratch.ensure(stride * nb)) != W3_OK) return rc;
+  if ((rc = d.scratch.ensure(stride * nb)) != W3_OK) return rc;
+  CK(cudaMemsetAsync(d.d_flag, 0, 4, d.stream));
+  CK(w3_launch_encode((const uint8_t *)d.in.p, bytes, (uint32_t)bs, (uint32_t)nb,
+                      (uint8_t *)d.scratch.p, stride, (uint32_t *)d.lens.p, d.d_flag, d.d_tab,
+                      d.sm_count, &ctx->opts, d.stream));
+  uint32_t flag = 0;
+  CK(cudaMemcpyAsync(&flag, d.d_flag, 4, cudaMemcpyDeviceToHost, d.stream));
+  CK(cudaMemcpyAsync(part.lens.data(), d.lens.p, nb * 4, cudaMemcpyDeviceToHost, d.stream));
+  CK(cudaStreamSynchronize(d.stream));
+  if (flag & W3_ERR_ABORT) return fail_msg(W3_E_CUDA, "encode kernel aborted (inter-warp wait timed out)");
+  const uint64_t *d_alt = nullptr;
+  if (flag & W3_ERR_OVERFLOW) {
+    std::vector<size_t> ov;
+    uint64_t need = 0;
+    for (size_t i = 0; i < nb; i++)
+      if (part.lens[i] > stride) { ov.push_back(i); need = std::max<uint64_t>(need, part.lens[i]); }
+    if (ov.empty() || need > MAX_STREAM) return fail_msg(W3_E_TOOBIG, "a block's stream is %llu bytes", (unsigned long long)need);
+    const size_t stride2 = round_up((size_t)need + 64, 16);
+    if ((rc = d.scratch2.ensure(stride2 * ov.size())) != W3_OK) return rc;
+    if ((rc = d.lens2.ensure(ov.size() * 4)) != W3_OK) return rc;
+    if ((rc = d.alt.ensure(nb * 8)) != W3_OK) return rc;
+    std::vector<uint64_t> alt(nb, 0);
     CK(cudaMemsetAsync(d.d_flag, 0, 4, d.stream));
-    CK(w3_launch_encode((const uint8_t *)d.in.p, bytes, (uint32_t)bs, (uint32_t)nb,
-                        (uint8_t *)d.scratch.p, stride, (uint32_t *)d.lens.p, d.d_flag, d.d_tab,
-                        d.sm_count, d.stream));
-    uint32_t flag = 0;
+    for (size_t j = 0; j < ov.size(); j++) {
+      const size_t i = ov[j], boff = i * bs, blen = std::min(bs, bytes - boff);
+      uint8_t *dst = (uint8_t *)d.scratch2.p + j * stride2;
+      alt[i] = (uint64_t)(uintptr_t)dst;
+      CK(w3_launch_encode((const uint8_t *)d.in.p + boff, blen, (uint32_t)bs, 1u, dst, stride2,
+                          (uint32_t *)d.lens2.p + j, d.d_flag, d.d_tab, d.sm_count, &ctx->opts, d.stream));
+    }
+    CK(cudaMemcpyAsync(d.alt.p, alt.data(), nb * 8, cudaMemcpyHostToDevice, d.stream));
     CK(cudaMemcpyAsync(&flag, d.d_flag, 4, cudaMemcpyDeviceToHost, d.stream));
-    CK(cudaMemcpyAsync(part.lens.data(), d.lens.p, nb * 4, cudaMemcpyDeviceToHost, d.stream));
     CK(cudaStreamSynchronize(d.stream));
-    if (flag & 2u) { snprintf(g_cuda_err, sizeof g_cuda_err, "encode kernel aborted (inter-warp wait timed out)"); return W3_E_CUDA; }
-    if (!flag) break;
-    if (attempt) { snprintf(g_cuda_err, sizeof g_cuda_err, "stream exceeded the 17n bound"); return W3_E_CUDA; }
-    stride = round_up(17 * bs + 64, 16);
+    if (flag) return fail_msg(W3_E_CUDA, "re-encoding an overflowed block failed (flag %u)", flag);
+    d_alt = (const uint64_t *)d.alt.p;
   }
   for (uint32_t l : part.lens) part.total += l;
   if ((rc = d.packed.ensure(part.total + 16)) != W3_OK) return rc;
   CK(w3_launch_pack((const uint8_t *)d.scratch.p, stride, (const uint32_t *)d.lens.p, (uint32_t)nb,
-                    (uint64_t *)d.offsets.p, (uint8_t *)d.packed.p, d.stream));
+                    (uint64_t *)d.offsets.p, d_alt, (uint8_t *)d.packed.p, d.stream));
   return W3_OK;
 }
 
@@ -342,9 +403,14 @@ int w3_compress(w3_ctx *ctx, const uint8_t *in, size_t n, size_t block_size, uin
                 uint8_t *out, size_t cap, size_t *out_len) {
   if (!ctx || !out_len || (!in && n) || (!out && cap)) return W3_E_ARG;
   const bool legacy = flags & W3_F_LEGACY;
-  if (legacy) block_size = std::max<size_t>(round_up(n, 4), 4);
+  if (legacy) {
+    /* the reference streams a file of any length (main.rs:96: u64); here one stream is one block */
+    if (n > MAX_BLOCK) return fail_msg(W3_E_TOOBIG, "a reference-format (w30i) file holds one stream: %zu bytes exceed the %zu-byte block limit", n, MAX_BLOCK);
+    block_size = std::max<size_t>(round_up(n, 4), 4);
+  }
   if (!block_size) block_size = W3_DEFAULT_BLOCK;
-  if ((block_size & 3) || block_size > MAX_BLOCK) return W3_E_ARG;
+  if (block_size & 3) return W3_E_ARG;
+  if (block_size > MAX_BLOCK) return fail_msg(W3_E_TOOBIG, "block size %zu exceeds %zu", block_size, MAX_BLOCK);
   std::lock_guard<std::mutex> lock(ctx->mu);
   /* the reference codes an empty file as one empty stream (0xff); keep that
    * in legacy form, and an empty container has zero blocks */
@@ -431,7 +497,8 @@ int w3_decompress(w3_ctx *ctx, const uint8_t *in, size_t n_in, uint8_t *out, siz
     /* one stream running to the end of the file; a short file decodes with
      * zero bits past its end, as ACReader does (io.rs:23-25) */
     bs = std::max<size_t>(round_up(n, 4), 4);
-    if (bs > MAX_BLOCK) return W3_E_ARG;
+    if (bs > MAX_BLOCK || n_in - HDR_LEGACY > MAX_STREAM)
+      return fail_msg(W3_E_TOOBIG, "reference-format stream of %zu bytes for %zu bytes of output: one stream is one block here", n_in - HDR_LEGACY, n);
     nb = n ? 1 : 0;
     hdr = HDR_LEGACY;
     offs = {0, n_in - hdr};
@@ -440,6 +507,8 @@ int w3_decompress(w3_ctx *ctx, const uint8_t *in, size_t n_in, uint8_t *out, siz
     bs = get_be32(in + 16);
     nb = get_be32(in + 20);
     if (!bs || (bs & 3) || bs > MAX_BLOCK || nb != (n + bs - 1) / bs) return W3_E_FORMAT;
+    for (size_t i = 0; i < nb && HDR_BLOCKS + (in[4] == 2 ? HDR_MODEL : 0) + 4 * (i + 1) <= n_in; i++)
+      if (get_be32(in + HDR_BLOCKS + (in[4] == 2 ? HDR_MODEL : 0) + 4 * i) > MAX_STREAM) return W3_E_FORMAT;
     const size_t fixed = HDR_BLOCKS + (in[4] == 2 ? HDR_MODEL : 0);
     hdr = fixed + 4 * nb;
     if (n_in < hdr) return W3_E_FORMAT;
@@ -478,12 +547,12 @@ int w3_decompress(w3_ctx *ctx, const uint8_t *in, size_t n_in, uint8_t *out, siz
     CK(cudaMemsetAsync(d.d_flag, 0, 4, d.stream));
     CK(w3_launch_decode((const uint8_t *)d.packed.p, (const uint64_t *)d.offsets.p, (uint32_t)nbg,
                         (uint32_t)bs, obytes, (uint8_t *)d.out.p, d.d_flag, d.d_tab, d.sm_count,
-                        d.stream));
+                        &ctx->opts, d.stream));
     uint32_t flag = 0;
     CK(cudaMemcpyAsync(&flag, d.d_flag, 4, cudaMemcpyDeviceToHost, d.stream));
     CK(cudaMemcpyAsync(out + o0, d.out.p, obytes, cudaMemcpyDeviceToHost, d.stream));
     CK(cudaStreamSynchronize(d.stream));
-    if (flag) { snprintf(g_cuda_err, sizeof g_cuda_err, "decode kernel aborted (flag %u)", flag); return (int)W3_E_CUDA; }
+    if (flag) return fail_msg(W3_E_CUDA, "decode kernel aborted (flag %u)", flag);
     return (int)W3_OK;
   });
 }

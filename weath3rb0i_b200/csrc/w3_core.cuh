@@ -50,6 +50,10 @@
 #define W3_NCELL2 (1 << W3_PB2)
 #define W3_FIX_THR 6 /* thresholds a fixed-latency lookup compares */
 
+/* bits of the device error word the codec kernels OR into */
+#define W3_ERR_OVERFLOW 1u /* a stream did not fit its scratch region */
+#define W3_ERR_ABORT 2u    /* a kernel gave up (bounded inter-warp wait, or a length it cannot handle) */
+
 W3_HD int w3_clz32(uint32_t v) {
 #if defined(__CUDA_ARCH__)
   return __clz((int)v);
@@ -126,6 +130,40 @@ W3_HD uint32_t w3_fsr_clamp(uint32_t lo, uint32_t hi, uint32_t sh) {
 #else
   if (sh > 32u) sh = 32u;
   return (uint32_t)(((((uint64_t)hi) << 32) | lo) >> sh);
+#endif
+}
+
+/* high word of (hi:lo) << (sh & 31) — __funnelshift_l */
+W3_HD uint32_t w3_fsl(uint32_t lo, uint32_t hi, uint32_t sh) {
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_l(lo, hi, sh);
+#else
+  sh &= 31u;
+  return sh ? (hi << sh) | (lo >> (32u - sh)) : hi;
+#endif
+}
+/* low word of (hi:lo) >> (sh & 31) — __funnelshift_r */
+W3_HD uint32_t w3_fsr(uint32_t lo, uint32_t hi, uint32_t sh) {
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(lo, hi, sh);
+#else
+  sh &= 31u;
+  return sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
+#endif
+}
+W3_HD uint32_t w3_bswap32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(v, 0, 0x0123);
+#else
+  return __builtin_bswap32(v);
+#endif
+}
+/* read-only global word (the streams and inputs are never written by the kernel that reads them) */
+W3_HD uint32_t w3_ldg32(const uint32_t *p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
 #endif
 }
 

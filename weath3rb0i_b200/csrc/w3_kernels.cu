@@ -374,6 +374,7 @@ w3_decode_blocks_warp(const uint8_t *__restrict__ comp, const uint64_t *__restri
 }
 
 #include "w3_team.cuh"
+#include "w3_lane.cuh"
 
 /* ------------------------------------------------------------------------ */
 /* stream compaction: offsets = exclusive scan of lens, then a packed copy   */
@@ -398,11 +399,15 @@ __global__ void w3_k_scan_lens(const uint32_t *__restrict__ lens, uint32_t n_blo
   for (uint32_t i = lo; i < hi; i++) { offsets[i] = run; run += lens[i]; }
 }
 
+/* alt (optional): per block, the address of its stream if it is not in its scratch region
+ * (blocks re-encoded after an overflow), 0 otherwise */
 __global__ void w3_k_pack(const uint8_t *__restrict__ scratch, uint64_t stride,
-                          const uint64_t *__restrict__ offsets, uint8_t *__restrict__ packed) {
+                          const uint64_t *__restrict__ offsets, const uint64_t *__restrict__ alt,
+                          uint8_t *__restrict__ packed) {
   const uint32_t blk = blockIdx.x;
   const uint64_t len = offsets[blk + 1] - offsets[blk];
   const uint8_t *src = scratch + (uint64_t)blk * stride;
+  if (alt && alt[blk]) src = reinterpret_cast<const uint8_t *>(alt[blk]);
   uint8_t *dst = packed + offsets[blk];
   for (uint64_t i = (uint64_t)blockIdx.y * blockDim.x + threadIdx.x; i < len;
        i += (uint64_t)gridDim.y * blockDim.x)
@@ -614,19 +619,27 @@ static inline int w3_pick_warps(uint32_t n_blocks, int sm_count) {
   return w;
 }
 
-/* W3_MODE=warp|team overrides the choice.  By default the team kernels (one CTA
- * per block: 3 resident per SM for encode, 1 for decode) run in as many waves as
- * it takes while that beats stacking 8 one-warp blocks on an SM — measured on
- * 1 GiB (profiles/r01_modes_1gib.txt): encode 840-1120 MB/s against 294-1075
- * up to 1024 blocks (warp kernels: 1586 at 4096 blocks), decode 260-277 against
- * 100-247 up to 683 blocks (warp kernels: 371 against 297 at 1024).
- * `max_per_sm` = blocks per SM up to which the team kernel is chosen. */
-static inline bool w3_use_team(uint32_t n_blocks, int sm_count, uint32_t max_per_sm) {
-  const char *m = getenv("W3_MODE");
-  if (m && !strcmp(m, "warp")) return false;
-  if (m && !strcmp(m, "team")) return true;
-  return n_blocks <= max_per_sm * (uint32_t)sm_count;
+/* Kernel families (w3_launch_opts.kernels forces one; 0 = by block count):
+ *   team   one CTA per block, the coder's chain in a warp of its own (w3_team.cuh): up to one
+ *          block per SM nothing is faster (69 / 109 cycles per coded bit, encode / decode).
+ *   many   more blocks than SMs.  Encode: the same teams, up to eight per CTA sharing one table
+ *          copy, so that every block is resident at once.  Decode: one LANE per block
+ *          (w3_lane.cuh) — an instruction costs the same for 1 or 32 active lanes.
+ *   warp   round 1's one-warp-per-block kernels, kept for comparison. */
+enum { W3_K_AUTO = 0, W3_K_TEAM = 1, W3_K_WARP = 2, W3_K_MANY = 3 };
+
+static inline uint32_t w3_ceil_div(uint32_t a, uint32_t b) { return (a + b - 1u) / b; }
+
+/* blocks a CTA takes at a time when every SM gets ceil(n_blocks / sm_count) blocks in as few,
+ * equally filled rounds as `cap` (what fits a CTA) allows */
+static inline uint32_t w3_per_cta(uint32_t n_blocks, int sm_count, uint32_t cap) {
+  const uint32_t q = w3_ceil_div(n_blocks, (uint32_t)sm_count);
+  const uint32_t rounds = w3_ceil_div(q, cap);
+  return w3_ceil_div(q, rounds);
 }
+
+#define W3_LANE_SMEM_MAX (227u * 1024u)
+static inline uint32_t w3_lane_cap(void) { return (W3_LANE_SMEM_MAX - (uint32_t)sizeof(w3_lane_tab)) / (W3_NCTX * 4u); }
 
 extern "C" {
 
@@ -646,10 +659,13 @@ cudaError_t w3_kernels_init(void) {
                            (int)w3_dense_dec_smem_bytes(W3_MAX_WARPS));
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(w3_encode_blocks_team, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)(sizeof(w3_smem_tab) + sizeof(w3_enc_team)));
+                           (int)(sizeof(w3_smem_tab) + W3_ENC_TEAM_MAXB * sizeof(w3_enc_team)));
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(w3_decode_blocks_team, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)(sizeof(w3_dec_tab) + sizeof(w3_dec_team)));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(w3_decode_blocks_lane, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(sizeof(w3_lane_tab) + w3_lane_cap() * W3_NCTX * 4u));
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(w3_k_hash_array, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)sizeof(w3_smem_tab));
@@ -658,27 +674,32 @@ cudaError_t w3_kernels_init(void) {
 cudaError_t w3_launch_encode(const uint8_t *d_in, uint64_t n_total, uint32_t block_size,
                              uint32_t n_blocks, uint8_t *d_scratch, uint64_t stride,
                              uint32_t *d_lens, uint32_t *d_overflow, const w3_hashtab *d_tab,
-                             int sm_count, cudaStream_t s) {
+                             int sm_count, const w3_launch_opts *opts, cudaStream_t s) {
   if (!n_blocks) return cudaSuccess;
-  if (w3_use_team(n_blocks, sm_count, 8u)) {
-    w3_encode_blocks_team<<<n_blocks, W3_ENC_TEAM_THREADS, sizeof(w3_smem_tab) + sizeof(w3_enc_team), s>>>(
+  const int k = opts ? opts->kernels : W3_K_AUTO;
+  if (k == W3_K_WARP) {
+    int warps = w3_pick_warps(n_blocks, sm_count);
+    uint32_t grid = (n_blocks + (uint32_t)warps - 1) / (uint32_t)warps;
+    w3_encode_blocks_warp<<<grid, warps * 32, w3_smem_bytes(warps), s>>>(
         d_in, n_total, block_size, n_blocks, d_scratch, stride, d_lens, d_overflow, d_tab);
     return cudaGetLastError();
   }
-  int warps = w3_pick_warps(n_blocks, sm_count);
-  uint32_t grid = (n_blocks + (uint32_t)warps - 1) / (uint32_t)warps;
-  w3_encode_blocks_warp<<<grid, warps * 32, w3_smem_bytes(warps), s>>>(
+  uint32_t teams = 1u;
+  if (k != W3_K_TEAM) teams = w3_per_cta(n_blocks, sm_count, W3_ENC_TEAM_MAXB);
+  if (opts && opts->enc_teams > 0) teams = (uint32_t)opts->enc_teams < W3_ENC_TEAM_MAXB ? (uint32_t)opts->enc_teams : W3_ENC_TEAM_MAXB;
+  w3_encode_blocks_team<<<w3_ceil_div(n_blocks, teams), W3_ENC_TEAM_THREADS * teams,
+                          sizeof(w3_smem_tab) + teams * sizeof(w3_enc_team), s>>>(
       d_in, n_total, block_size, n_blocks, d_scratch, stride, d_lens, d_overflow, d_tab);
   return cudaGetLastError();
 }
 
 cudaError_t w3_launch_pack(const uint8_t *d_scratch, uint64_t stride, const uint32_t *d_lens,
-                           uint32_t n_blocks, uint64_t *d_offsets, uint8_t *d_packed,
-                           cudaStream_t s) {
+                           uint32_t n_blocks, uint64_t *d_offsets, const uint64_t *d_alt,
+                           uint8_t *d_packed, cudaStream_t s) {
   w3_k_scan_lens<<<1, 1024, 0, s>>>(d_lens, n_blocks, d_offsets);
   if (n_blocks) {
     dim3 grid(n_blocks, 32);
-    w3_k_pack<<<grid, 256, 0, s>>>(d_scratch, stride, d_offsets, d_packed);
+    w3_k_pack<<<grid, 256, 0, s>>>(d_scratch, stride, d_offsets, d_alt, d_packed);
   }
   return cudaGetLastError();
 }
@@ -692,18 +713,39 @@ cudaError_t w3_launch_scan(const uint32_t *d_lens, uint32_t n_blocks, uint64_t *
 cudaError_t w3_launch_decode(const uint8_t *d_comp, const uint64_t *d_offsets, uint32_t n_blocks,
                              uint32_t block_size, uint64_t n_total, uint8_t *d_out,
                              uint32_t *d_err, const w3_hashtab *d_tab, int sm_count,
-                             cudaStream_t s) {
+                             const w3_launch_opts *opts, cudaStream_t s) {
   if (!n_blocks) return cudaSuccess;
-  if (w3_use_team(n_blocks, sm_count, 5u)) {
+  int k = opts ? opts->kernels : W3_K_AUTO;
+  /* the lane decoder counts stream bits in 32 bits: blocks it cannot be sure about go to the team kernel */
+  const bool lane_ok = block_size <= (16u << 20);
+  if (k == W3_K_AUTO) k = (n_blocks > (uint32_t)sm_count && lane_ok) ? W3_K_MANY : W3_K_TEAM;
+  if (k == W3_K_MANY && !lane_ok) k = W3_K_TEAM;
+  if (k == W3_K_TEAM) {
     w3_decode_blocks_team<<<n_blocks, W3_DEC_TEAM_THREADS,
                             sizeof(w3_dec_tab) + sizeof(w3_dec_team), s>>>(
         d_comp, d_offsets, n_blocks, block_size, n_total, d_out, d_err, d_tab);
     return cudaGetLastError();
   }
-  int warps = w3_pick_warps(n_blocks, sm_count);
-  uint32_t grid = (n_blocks + (uint32_t)warps - 1) / (uint32_t)warps;
-  w3_decode_blocks_warp<<<grid, warps * 32, w3_dense_dec_smem_bytes(warps), s>>>(
-      d_comp, d_offsets, n_blocks, block_size, n_total, d_out, d_tab);
+  if (k == W3_K_WARP) {
+    int warps = w3_pick_warps(n_blocks, sm_count);
+    uint32_t grid = (n_blocks + (uint32_t)warps - 1) / (uint32_t)warps;
+    w3_decode_blocks_warp<<<grid, warps * 32, w3_dense_dec_smem_bytes(warps), s>>>(
+        d_comp, d_offsets, n_blocks, block_size, n_total, d_out, d_tab);
+    return cudaGetLastError();
+  }
+  /* lane per block: `resident` blocks per CTA at a time, spread over `warps` warps (one per SM
+   * sub-partition by default) of `lanes` active lanes */
+  const uint32_t per = w3_per_cta(n_blocks, sm_count, w3_lane_cap());
+  uint32_t warps = per < 4u ? per : 4u;
+  if (opts && opts->lane_warps > 0) warps = (uint32_t)opts->lane_warps < W3_LANE_MAX_WARPS ? (uint32_t)opts->lane_warps : W3_LANE_MAX_WARPS;
+  if (warps > per) warps = per;
+  uint32_t lanes = w3_ceil_div(per, warps);
+  while (warps * lanes > w3_lane_cap()) lanes--; /* rounding up may overshoot what fits */
+  const uint32_t resident = warps * lanes;
+  uint32_t grid = w3_ceil_div(n_blocks, resident);
+  if (grid > (uint32_t)sm_count) grid = (uint32_t)sm_count;
+  w3_decode_blocks_lane<<<grid, warps * 32u, sizeof(w3_lane_tab) + (size_t)resident * W3_NCTX * 4u, s>>>(
+      d_comp, d_offsets, n_blocks, block_size, n_total, d_out, d_err, d_tab, lanes);
   return cudaGetLastError();
 }
 

@@ -7,6 +7,13 @@
 
 struct w3_hashtab;
 
+/* which kernel family codes the blocks: the context's options (w3_ctx_set_option), 0 = the launcher decides */
+struct w3_launch_opts {
+  int kernels;    /* W3_OPT_KERNELS: 0 auto, 1 team (one block per CTA), 2 warp (one warp per block), 3 many-block (teams sharing a CTA / lane per block) */
+  int enc_teams;  /* W3_OPT_ENC_TEAMS: teams per CTA of the team encoder, 0 auto */
+  int lane_warps; /* W3_OPT_LANE_WARPS: warps per CTA of the lane decoder, 0 auto */
+};
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -15,16 +22,17 @@ cudaError_t w3_launch_build_table(struct w3_hashtab *d_tab, cudaStream_t s);
 cudaError_t w3_launch_encode(const uint8_t *d_in, uint64_t n_total, uint32_t block_size,
                              uint32_t n_blocks, uint8_t *d_scratch, uint64_t stride,
                              uint32_t *d_lens, uint32_t *d_overflow,
-                             const struct w3_hashtab *d_tab, int sm_count, cudaStream_t s);
+                             const struct w3_hashtab *d_tab, int sm_count,
+                             const struct w3_launch_opts *opts, cudaStream_t s);
 cudaError_t w3_launch_scan(const uint32_t *d_lens, uint32_t n_blocks, uint64_t *d_offsets,
                            cudaStream_t s);
 cudaError_t w3_launch_pack(const uint8_t *d_scratch, uint64_t stride, const uint32_t *d_lens,
-                           uint32_t n_blocks, uint64_t *d_offsets, uint8_t *d_packed,
-                           cudaStream_t s);
+                           uint32_t n_blocks, uint64_t *d_offsets, const uint64_t *d_alt,
+                           uint8_t *d_packed, cudaStream_t s);
 cudaError_t w3_launch_decode(const uint8_t *d_comp, const uint64_t *d_offsets, uint32_t n_blocks,
                              uint32_t block_size, uint64_t n_total, uint8_t *d_out,
                              uint32_t *d_err, const struct w3_hashtab *d_tab, int sm_count,
-                             cudaStream_t s);
+                             const struct w3_launch_opts *opts, cudaStream_t s);
 /* StationaryModel::new on the device: d_cnt needs ceil(n / 1024) * 8 u16 */
 cudaError_t w3_launch_train(const uint8_t *d_in, uint64_t n, uint16_t *d_cnt, uint16_t *d_table,
                             int sm_count, cudaStream_t s);

@@ -59,8 +59,6 @@
 #define W3_ATTEMPTS_PER_TRIP 16u /* decoder: straight-line attempts per loop trip (<= 32) */
 #endif
 
-#define W3_ERR_OVERFLOW 1u
-#define W3_ERR_ABORT 2u
 
 /* shared-memory words by 32-bit address: keeps the address in a register
  * (no generic-pointer arithmetic per access) and fixes the issue order */
@@ -117,26 +115,36 @@ struct w3_enc_team {
   uint32_t pad[2];
 };
 
-#define W3_ENC_TEAM_THREADS 96
+#define W3_ENC_TEAM_THREADS 96 /* per team: coder, model and writer warp */
+/* Teams per CTA.  One team per CTA leaves an SM at three resident blocks (the
+ * 48 KiB table copy is per CTA); with up to eight teams sharing one copy, 1024
+ * blocks (1 GiB in 1 MiB blocks) are resident at once instead of running in
+ * 2.3 waves, and the 21-24 warps of a CTA fill the issue slots a lone team of
+ * three leaves idle. */
+#define W3_ENC_TEAM_MAXB 8u
 
-__global__ void __launch_bounds__(W3_ENC_TEAM_THREADS)
+__global__ void __launch_bounds__(W3_ENC_TEAM_THREADS * W3_ENC_TEAM_MAXB, 1)
 w3_encode_blocks_team(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t block_size,
                       uint32_t n_blocks, uint8_t *__restrict__ scratch, uint64_t stride,
                       uint32_t *__restrict__ lens, uint32_t *__restrict__ err,
                       const w3_hashtab *__restrict__ tab) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   w3_smem_tab *st = reinterpret_cast<w3_smem_tab *>(smem_raw);
-  w3_enc_team *tm = reinterpret_cast<w3_enc_team *>(smem_raw + sizeof(w3_smem_tab));
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t team = (threadIdx.x >> 5) / 3u, warp = (threadIdx.x >> 5) % 3u, n_teams = blockDim.x / W3_ENC_TEAM_THREADS;
+  w3_enc_team *tm = reinterpret_cast<w3_enc_team *>(smem_raw + sizeof(w3_smem_tab)) + team;
 
   w3_load_tab(st, tab);
-  for (uint32_t i = threadIdx.x; i < W3_NCTX; i += blockDim.x) tm->stats[i] = 0u;
-  if (threadIdx.x == 0) {
+  {
+    w3_enc_team *t0 = reinterpret_cast<w3_enc_team *>(smem_raw + sizeof(w3_smem_tab));
+    for (uint32_t i = threadIdx.x; i < n_teams * W3_NCTX; i += blockDim.x) t0[i / W3_NCTX].stats[i % W3_NCTX] = 0u;
+  }
+  if (warp == 0 && lane == 0) {
     tm->prod_done = 0; tm->cons_done = 0; tm->out_done = 0; tm->wr_done = 0; tm->abort_flag = 0;
   }
   __syncthreads();
 
-  const uint32_t blk = blockIdx.x;
+  const uint32_t blk = blockIdx.x * n_teams + team;
   if (blk >= n_blocks) return;
   const uint64_t off = (uint64_t)blk * block_size;
   const uint32_t n = (uint32_t)(n_total - off < block_size ? n_total - off : block_size);
@@ -661,12 +669,19 @@ w3_decode_blocks_team(const uint8_t *__restrict__ comp, const uint64_t *__restri
     const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(sp) & 3u);
     const uint32_t *ab = reinterpret_cast<const uint32_t *>(sp - sh);
     const uint32_t sel = ((sh + 3u) | ((sh + 2u) << 4) | ((sh + 1u) << 8) | (sh << 12));
-    uint32_t fed = 0, spins = 0;
+    uint32_t fed = 0, spins = 0, seen = 0;
     for (;;) {
       const uint32_t c = w3_lds(cons_a);
       if (c == 0xFFFFFFFFu || w3_lds(abort_a)) break;
       if ((int32_t)(fed - c) > (int32_t)(W3_SRING - 40u)) { /* ring full */
-        if (++spins > W3_SPIN_LIMIT) {
+        /* A full ring is no fault: highly compressible data decodes tens of millions of bits per
+         * 1024 stream bits (p = 65535/65536 costs 2.2e-5 bits).  Only a decoder that has stopped
+         * decoding is one, so the watchdog counts polls without progress in its published bit
+         * count, not polls of the ring. */
+        const uint32_t bits = w3_lds(pub_a + 4u);
+        spins = bits == seen ? spins + 1u : 0u;
+        seen = bits;
+        if (spins > W3_SPIN_LIMIT) {
 #ifdef W3_DEBUG
           if (lane == 0) printf("[w3] feeder timeout fed %u cons %u\n", fed, c);
 #endif
