@@ -147,6 +147,23 @@ int w3_selftest_ac_encode(w3_ctx *ctx, const uint8_t *in, size_t n_in, const uin
 int w3_selftest_ac_decode(w3_ctx *ctx, const uint8_t *in, size_t n_in, const uint16_t *probs,
                           size_t n_probs, uint8_t *out, size_t cap);
 
+/* ---- Tier B unit self-tests -------------------------
+ * The reference's state table and hash-slot cells have no caller there (private modules,
+ * src/lib.rs:11-13); these entry points expose the device implementations (csrc/w3_tierb.cuh)
+ * so that tests can compare them with the reference's own dumps. */
+/* NaiveStateTable (src/state_table/naive.rs:9-115) as built on the device: which = 0 the 3963-entry
+ * table (docs/state_table/state_table.csv), 1 the 990-entry auxiliary table (aux_state_table.csv).
+ * Each array receives n entries: StateTable::next(s, 0), next(s, 1), p(s) (src/state_table/mod.rs:41-49). */
+int w3_selftest_state_table(w3_ctx *ctx, int which, uint16_t *next0, uint16_t *next1, uint16_t *prob, size_t n);
+/* Replays n_ops cell operations in order on the device over n_cells 96-byte cells (src/hashmap.rs:32-129;
+ * in/out: cells).  op = {code | cell << 8, a, b, c}, two result words per op:
+ *   0 Slot::get_idx(id a, bit_id b, nib_ctx c) -> abs_idx, parity      1 Slot::get_state(a, b, c) -> state
+ *   2 Slot::set_state(id | bit_id << 8 | nib_ctx << 16, state b)        3 Cell::get_slot(hash = b:a) -> slot id
+ *   4 Slot::set_nib(id | nib << 8, s0 | s1 << 16, s2 | s3 << 16)        5 Slot::get_nib(id | nib << 8) -> packed states
+ *   6 HashMap::get_slot's cell index (hash = b:a, log_cell_count c) -> index low, high */
+int w3_selftest_hashslots(w3_ctx *ctx, const uint32_t *ops, size_t n_ops, uint8_t *cells, size_t n_cells,
+                          uint32_t *results);
+
 const char *w3_strerror(int code);
 const char *w3_last_cuda_error(void);
 const char *w3_version(void);

@@ -127,6 +127,27 @@ int w3o_decompress_blocks_mt(const uint8_t *in, size_t in_stride,
                              const uint32_t *in_lens, uint8_t *out, size_t n,
                              size_t block_size, int n_threads);
 
+/* ---- Tier B: state table and hash slots (w3_tierb_oracle.c) --------------
+ * Dead code in the reference (no caller), pinned by its own dumps:
+ * docs/state_table/state_table.csv, aux_state_table.csv, docs/hashslots.md:69-133. */
+int w3o_state_table_size(void);      /* 3963 — src/state_table/naive.rs:11 */
+int w3o_aux_state_table_size(void);  /* 990  — naive.rs:10 */
+uint16_t w3o_state_next(uint16_t state, int bit); /* StateTable::next — src/state_table/mod.rs:41-43 */
+uint16_t w3o_state_p(uint16_t state);             /* StateTable::p    — mod.rs:45-47 */
+uint16_t w3o_aux_state_next(uint16_t state, int bit); /* gen_auxiliary_table — naive.rs:50-75 */
+uint16_t w3o_aux_state_p(uint16_t state);
+void w3o_state_next4(const uint16_t states[4], uint8_t nib, uint16_t out[4]); /* mod.rs:5-12 */
+void w3o_state_p4(const uint16_t states[4], uint16_t out[4]);                 /* mod.rs:15-22 */
+uint32_t w3o_hashmap_log_cell_count(uint64_t size);                    /* HashMap::new — src/hashmap.rs:7-10 */
+uint64_t w3o_hashmap_cell_index(uint64_t hash, uint32_t log_cell_count); /* HashMap::get_slot — :25-28 */
+int w3o_cell_get_slot(const uint8_t cell[96], uint64_t hash);          /* Cell::get_slot — :43-71 */
+void w3o_slot_get_idx(int id, int bit_id, int nib_ctx, uint32_t *abs_idx, int *parity); /* :80-84 */
+uint16_t w3o_slot_get_state(const uint8_t cell[96], int id, int bit_id, int nib_ctx);   /* :86-97 */
+void w3o_slot_set_state(uint8_t cell[96], int id, int bit_id, int nib_ctx, uint16_t new_state); /* :99-112 */
+void w3o_slot_set_nib(uint8_t cell[96], int id, uint8_t nib, const uint16_t s[4]); /* :114-119 */
+void w3o_slot_get_nib(const uint8_t cell[96], int id, uint8_t nib, uint16_t s[4]); /* :121-128 */
+uint16_t w3o_opinion_mix2(uint16_t p1, uint16_t p2); /* OpinionMixer2::mix — src/mixers/opinion_mixer2.rs:5-10 */
+
 #ifdef __cplusplus
 }
 #endif

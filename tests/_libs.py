@@ -26,7 +26,7 @@ def _newer(target, *srcs):
 def build_oracle():
     d = os.path.join(ROOT, "oracle")
     so = os.path.join(d, "libw3oracle.so")
-    if not _newer(so, os.path.join(d, "w3_oracle.c"), os.path.join(d, "w3_oracle.h")):
+    if not _newer(so, *(os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith((".c", ".h")) or f == "Makefile")):
         subprocess.check_call(["make", "-s", "-C", d])
     return so
 
@@ -34,10 +34,9 @@ def build_oracle():
 def build_hostsim():
     d = os.path.join(ROOT, "tests", "hostsim")
     so = os.path.join(d, "libw3hostsim.so")
-    core = os.path.join(ROOT, "weath3rb0i_b200", "csrc", "w3_core.cuh")
-    lane = os.path.join(ROOT, "weath3rb0i_b200", "csrc", "w3_lane.cuh")
+    csrc = os.path.join(ROOT, "weath3rb0i_b200", "csrc")
     src = os.path.join(d, "w3_hostsim.cpp")
-    if not _newer(so, src, core, lane):
+    if not _newer(so, src, *(os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh"))):
         subprocess.check_call(
             ["g++", "-O2", "-std=c++17", "-Wall", "-shared", "-fPIC", "-o", so, src]
         )
@@ -78,6 +77,24 @@ def load_oracle():
     o.w3o_compress_file.argtypes = [u8p, sz, C.c_void_p, sz, C.POINTER(sz)]
     o.w3o_decompress_file.argtypes = [u8p, sz, C.c_void_p, sz, C.POINTER(sz)]
     o.w3o_ctx_trace.argtypes = [u8p, sz, u16p]
+    o.w3o_state_next.restype = o.w3o_state_p.restype = o.w3o_aux_state_next.restype = o.w3o_aux_state_p.restype = C.c_uint16
+    o.w3o_state_next.argtypes = o.w3o_aux_state_next.argtypes = [C.c_uint16, C.c_int]
+    o.w3o_state_p.argtypes = o.w3o_aux_state_p.argtypes = [C.c_uint16]
+    o.w3o_state_next4.argtypes = [u16p, C.c_uint8, u16p]
+    o.w3o_state_p4.argtypes = [u16p, u16p]
+    o.w3o_hashmap_log_cell_count.restype = C.c_uint32
+    o.w3o_hashmap_log_cell_count.argtypes = [C.c_uint64]
+    o.w3o_hashmap_cell_index.restype = C.c_uint64
+    o.w3o_hashmap_cell_index.argtypes = [C.c_uint64, C.c_uint32]
+    o.w3o_cell_get_slot.argtypes = [C.c_void_p, C.c_uint64]
+    o.w3o_slot_get_idx.argtypes = [C.c_int, C.c_int, C.c_int, u32p, C.POINTER(C.c_int)]
+    o.w3o_slot_get_state.restype = C.c_uint16
+    o.w3o_slot_get_state.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    o.w3o_slot_set_state.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint16]
+    o.w3o_slot_set_nib.argtypes = [C.c_void_p, C.c_int, C.c_uint8, u16p]
+    o.w3o_slot_get_nib.argtypes = [C.c_void_p, C.c_int, C.c_uint8, u16p]
+    o.w3o_opinion_mix2.restype = C.c_uint16
+    o.w3o_opinion_mix2.argtypes = [C.c_uint16, C.c_uint16]
     o.w3o_compress_blocks_mt.argtypes = [C.c_void_p, sz, sz, C.c_void_p, sz, C.c_void_p, C.c_int]
     o.w3o_decompress_blocks_mt.argtypes = [C.c_void_p, sz, C.c_void_p, C.c_void_p, sz, sz, C.c_int]
     return o
@@ -181,6 +198,14 @@ class HostSim:
         h.hs_counter_p_sweep.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
         h.hs_compress_block.argtypes = [C.c_void_p, C.c_char_p, sz, C.c_void_p, sz, C.POINTER(sz)]
         h.hs_decompress_block.argtypes = [C.c_void_p, C.c_char_p, sz, C.c_void_p, sz]
+        h.hs_state_entry.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_uint16)]
+        h.hs_slot_get_state.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
+        h.hs_slot_set_state.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+        h.hs_cell_get_slot.argtypes = [C.c_void_p, C.c_uint64]
+        h.hs_slot_set_nib.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint16)]
+        h.hs_slot_get_nib.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint16)]
+        h.hs_cell_index.restype = C.c_uint64
+        h.hs_cell_index.argtypes = [C.c_uint64, C.c_uint32]
         h.hs_lane_decode_block.argtypes = [C.c_void_p, C.c_char_p, sz, C.c_uint, C.c_uint8, C.c_void_p, sz]
         self.lib = h
         self.table = (C.c_uint16 * 8)(*table)

@@ -11,6 +11,7 @@
 
 #include "../../weath3rb0i_b200/csrc/w3_core.cuh"
 #include "../../weath3rb0i_b200/csrc/w3_lane.cuh"
+#include "../../weath3rb0i_b200/csrc/w3_tierb.cuh"
 
 extern "C" {
 
@@ -227,5 +228,19 @@ int hs_lane_decode_block(const w3_hashtab *tab, const uint8_t *in, size_t n_in, 
   memcpy(out, dst.data(), n_out);
   return 0;
 }
+
+/* ---- w3_tierb.cuh on the CPU -------------------------------------------------------------- */
+void hs_state_entry(uint32_t which, uint32_t i, uint16_t out[3]) {
+  const w3_state_entry e = which ? w3_aux_state_entry(i) : w3_state_entry_of(i);
+  out[0] = e.next[0]; out[1] = e.next[1]; out[2] = e.prob;
+}
+uint32_t hs_slot_idx(uint32_t id, uint32_t bit_id, uint32_t nib_ctx) { return w3_slot_idx(id, bit_id, nib_ctx); }
+uint32_t hs_slot_get_state(const uint8_t *cell, uint32_t id, uint32_t bit_id, uint32_t nib_ctx) { return w3_slot_get_state(cell, id, bit_id, nib_ctx); }
+void hs_slot_set_state(uint8_t *cell, uint32_t id, uint32_t bit_id, uint32_t nib_ctx, uint32_t st) { w3_slot_set_state(cell, id, bit_id, nib_ctx, st); }
+uint32_t hs_cell_get_slot(const uint8_t *cell, uint64_t hash) { return w3_cell_get_slot(cell, hash); }
+void hs_slot_set_nib(uint8_t *cell, uint32_t id, uint32_t nib, const uint16_t *s) { w3_slot_set_nib(cell, id, nib, s); }
+void hs_slot_get_nib(const uint8_t *cell, uint32_t id, uint32_t nib, uint16_t *s) { w3_slot_get_nib(cell, id, nib, s); }
+uint64_t hs_cell_index(uint64_t hash, uint32_t log_cell_count) { return w3_cell_index(hash, log_cell_count); }
+uint32_t hs_opinion_mix2(uint32_t p1, uint32_t p2) { return w3_opinion_mix2(p1, p2); }
 
 } /* extern "C" */

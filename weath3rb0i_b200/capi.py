@@ -24,6 +24,7 @@ SYMBOLS = (
     "w3_compress", "w3_decompress", "w3_decompressed_size",
     "w3_encode_device", "w3_pack_device", "w3_decode_device",
     "w3_selftest_achash", "w3_selftest_counter_p", "w3_probe_sector_gather", "w3_selftest_ac_encode", "w3_selftest_ac_decode",
+    "w3_selftest_state_table", "w3_selftest_hashslots",
     "w3_strerror", "w3_last_cuda_error", "w3_version",
 )
 
@@ -73,6 +74,8 @@ def load():
     lib.w3_probe_sector_gather.argtypes = [vp, sz, C.POINTER(C.c_double)]
     lib.w3_selftest_ac_encode.argtypes = [vp, u8p, sz, vp, sz, u8p, sz, C.POINTER(sz)]
     lib.w3_selftest_ac_decode.argtypes = [vp, u8p, sz, vp, sz, u8p, sz]
+    lib.w3_selftest_state_table.argtypes = [vp, C.c_int, vp, vp, vp, sz]
+    lib.w3_selftest_hashslots.argtypes = [vp, vp, sz, vp, sz, vp]
     for f in ("w3_strerror", "w3_last_cuda_error", "w3_version"):
         getattr(lib, f).restype = C.c_char_p
     lib.w3_strerror.argtypes = [C.c_int]
@@ -218,6 +221,25 @@ class Context:
         r = C.c_double(0.0)
         check(self.lib.w3_probe_sector_gather(self.handle, buffer_bytes, C.byref(r)))
         return r.value
+
+    def state_table(self, which: int = 0):
+        """(next0, next1, prob) lists of the device-built NaiveStateTable (0) / auxiliary table (1)."""
+        n = 3963 if which == 0 else 990
+        a, b, p = ((C.c_uint16 * n)() for _ in range(3))
+        check(self.lib.w3_selftest_state_table(self.handle, which, C.addressof(a), C.addressof(b), C.addressof(p), n))
+        return list(a), list(b), list(p)
+
+    def hashslot_ops(self, ops, cells: bytearray):
+        """Replays cell operations [(code, cell, a, b, c), ...] on the device; returns the result
+        pairs and updates `cells` (n x 96 bytes) in place."""
+        n = len(ops)
+        flat = (C.c_uint32 * (4 * max(n, 1)))()
+        for i, (code, cell, a, b, c) in enumerate(ops):
+            flat[4 * i:4 * i + 4] = [code | (cell << 8), a, b, c]
+        buf = (C.c_uint8 * len(cells)).from_buffer(cells)
+        res = (C.c_uint32 * (2 * max(n, 1)))()
+        check(self.lib.w3_selftest_hashslots(self.handle, C.addressof(flat), n, C.addressof(buf), len(cells) // 96, C.addressof(res)))
+        return [(res[2 * i], res[2 * i + 1]) for i in range(n)]
 
     def ac_encode_probs(self, data: bytes, probs) -> bytes:
         n = len(probs)

@@ -21,6 +21,7 @@
 #include "../../include/w3_codec.h"
 #include "w3_core.cuh"
 #include "w3_kernels.h"
+#include "w3_tierb.cuh"
 
 static thread_local char g_cuda_err[256] = "";
 static char g_cuda_err_any[256] = ""; /* the last message of any thread: the per-device worker threads' */
@@ -668,6 +669,44 @@ int w3_selftest_ac_decode(w3_ctx *ctx, const uint8_t *in, size_t n_in, const uin
   CK(w3_launch_ac_decode_probs((const uint8_t *)d.in.p, (uint32_t)n_in, (const uint16_t *)d.scratch.p,
                                (uint32_t)n_probs, (uint8_t *)d.out.p, d.stream));
   CK(cudaMemcpyAsync(out, d.out.p, (n_probs + 7) / 8, cudaMemcpyDeviceToHost, d.stream));
+  CK(cudaStreamSynchronize(d.stream));
+  return W3_OK;
+}
+
+int w3_selftest_state_table(w3_ctx *ctx, int which, uint16_t *next0, uint16_t *next1, uint16_t *prob, size_t n) {
+  const size_t size = which == 0 ? W3_ST_SIZE : W3_ST_SUB;
+  if (!ctx || (which != 0 && which != 1) || !next0 || !next1 || !prob || n > size) return W3_E_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  w3_dev &d = ctx->d[0];
+  CK(cudaSetDevice(d.ordinal));
+  int rc;
+  if ((rc = d.scratch.ensure((W3_ST_SIZE + W3_ST_SUB) * sizeof(w3_state_entry))) != W3_OK) return rc;
+  w3_state_entry *t = (w3_state_entry *)d.scratch.p, *aux = t + W3_ST_SIZE;
+  CK(w3_launch_build_state_table(t, aux, d.stream));
+  std::vector<w3_state_entry> h(size);
+  CK(cudaMemcpyAsync(h.data(), which == 0 ? t : aux, size * sizeof(w3_state_entry), cudaMemcpyDeviceToHost, d.stream));
+  CK(cudaStreamSynchronize(d.stream));
+  for (size_t i = 0; i < n; i++) { next0[i] = h[i].next[0]; next1[i] = h[i].next[1]; prob[i] = h[i].prob; }
+  return W3_OK;
+}
+
+int w3_selftest_hashslots(w3_ctx *ctx, const uint32_t *ops, size_t n_ops, uint8_t *cells, size_t n_cells,
+                          uint32_t *results) {
+  if (!ctx || !ops || !cells || !results || !n_cells || n_ops > 0x7FFFFFFF) return W3_E_ARG;
+  for (size_t i = 0; i < n_ops; i++)
+    if ((ops[4 * i] >> 8) >= n_cells || (ops[4 * i] & 0xFFu) > 6u) return W3_E_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  w3_dev &d = ctx->d[0];
+  CK(cudaSetDevice(d.ordinal));
+  int rc;
+  if ((rc = d.in.ensure(n_ops * 16 + 16)) != W3_OK) return rc;
+  if ((rc = d.scratch.ensure(n_cells * W3_CELL_BYTES)) != W3_OK) return rc;
+  if ((rc = d.out.ensure(n_ops * 8 + 16)) != W3_OK) return rc;
+  CK(cudaMemcpyAsync(d.in.p, ops, n_ops * 16, cudaMemcpyHostToDevice, d.stream));
+  CK(cudaMemcpyAsync(d.scratch.p, cells, n_cells * W3_CELL_BYTES, cudaMemcpyHostToDevice, d.stream));
+  CK(w3_launch_hashslot_ops((const uint32_t *)d.in.p, (uint32_t)n_ops, (uint8_t *)d.scratch.p, (uint32_t *)d.out.p, d.stream));
+  CK(cudaMemcpyAsync(results, d.out.p, n_ops * 8, cudaMemcpyDeviceToHost, d.stream));
+  CK(cudaMemcpyAsync(cells, d.scratch.p, n_cells * W3_CELL_BYTES, cudaMemcpyDeviceToHost, d.stream));
   CK(cudaStreamSynchronize(d.stream));
   return W3_OK;
 }

@@ -6,6 +6,7 @@
 #define W3_MAX_WARPS 8 /* blocks (= warps) sharing one CTA's copy of the threshold table */
 
 struct w3_hashtab;
+struct w3_state_entry;
 
 /* which kernel family codes the blocks: the context's options (w3_ctx_set_option), 0 = the launcher decides */
 struct w3_launch_opts {
@@ -46,6 +47,9 @@ cudaError_t w3_launch_ac_encode_probs(const uint8_t *d_in, const uint16_t *d_pro
                                       uint32_t *d_out_len, cudaStream_t s);
 cudaError_t w3_launch_ac_decode_probs(const uint8_t *d_in, uint32_t n_in, const uint16_t *d_probs,
                                       uint32_t n_probs, uint8_t *d_out, cudaStream_t s);
+/* Tier B (w3_tierb.cu): NaiveStateTable built on the device; the hash-slot unit self-test */
+cudaError_t w3_launch_build_state_table(struct w3_state_entry *d_table, struct w3_state_entry *d_aux, cudaStream_t s);
+cudaError_t w3_launch_hashslot_ops(const uint32_t *d_ops, uint32_t n_ops, uint8_t *d_cells, uint32_t *d_res, cudaStream_t s);
 #ifdef __cplusplus
 }
 #endif
