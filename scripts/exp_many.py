@@ -2,7 +2,7 @@
 (device-resident input, CUDA events) for a list of launch options and says whether the round trip
 matched and whether the packed streams equal those of the first configuration.  Never a bench number.
 
-usage: python scripts/exp_many.py MIB BLOCK_KIB "kernels:enc_teams:lane_warps" ...
+usage: python scripts/exp_many.py MIB BLOCK_KIB "kernels:enc_teams:lane_warps[:lane_form]" ...
 """
 import hashlib
 import os
@@ -50,8 +50,9 @@ def timed(fn, reps):
 first = None
 print(f"# {mib} MiB, {block >> 10} KiB blocks, {n_blocks} blocks", flush=True)
 for cfg in configs:
-    k, teams, warps = cfg.split(":")
+    k, teams, warps, *rest = cfg.split(":")
     ctx.set_kernels(k)
+    ctx.set_option(capi.W3_OPT_LANE_FORM, int(rest[0]) if rest else 0)
     ctx.set_option(capi.W3_OPT_ENC_TEAMS, int(teams))
     ctx.set_option(capi.W3_OPT_LANE_WARPS, int(warps))
     d_flag.zero_()

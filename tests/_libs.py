@@ -207,6 +207,7 @@ class HostSim:
         h.hs_cell_index.restype = C.c_uint64
         h.hs_cell_index.argtypes = [C.c_uint64, C.c_uint32]
         h.hs_lane_decode_block.argtypes = [C.c_void_p, C.c_char_p, sz, C.c_uint, C.c_uint8, C.c_void_p, sz]
+        h.hs_pair_decode_block.argtypes = [C.c_void_p, C.c_char_p, sz, C.c_uint, C.c_uint8, C.c_void_p, sz]
         self.lib = h
         self.table = (C.c_uint16 * 8)(*table)
         self.max_bits = max_bits
@@ -235,10 +236,13 @@ class HostSim:
         self.lib.hs_decompress_block(self.tab, stream, len(stream), out, n_out)
         return out.raw[:n_out]
 
-    def lane_decode_block(self, stream: bytes, n_out: int, misalign: int = 0, junk: int = 0xA5) -> bytes:
-        """w3_lane.cuh's per-lane decoder (what w3_decode_blocks_lane runs in every lane)."""
+    def lane_decode_block(self, stream: bytes, n_out: int, misalign: int = 0, junk: int = 0xA5, pair: bool = False) -> bytes:
+        """w3_lane.cuh's per-lane decoder (what w3_decode_blocks_lane runs in every lane), or its
+        pair form (w3_decode_blocks_pair: two lanes per block in lockstep)."""
         out = C.create_string_buffer(max(n_out, 1))
-        self.lib.hs_lane_decode_block(self.tab, stream, len(stream), misalign, junk, out, n_out)
+        fn = self.lib.hs_pair_decode_block if pair else self.lib.hs_lane_decode_block
+        rc = fn(self.tab, stream, len(stream), misalign, junk, out, n_out)
+        assert rc == 0, rc
         return out.raw[:n_out]
 
     def thresholds(self):

@@ -79,6 +79,7 @@ uint64_t hs_counter_p_sweep(uint32_t c0_lo, uint32_t c0_hi, uint32_t step) {
   for (uint32_t c0 = c0_lo; c0 < c0_hi; c0 += step)
     for (uint32_t c1 = 0; c1 <= 65534; c1++) {
       bad += w3_counter_p(c0, c1) != w3_counter_p_u64(c0, c1);
+      bad += w3_counter_p1(c0, c1) != w3_counter_p_u64(c0, c1);
       const uint32_t slot = c0 | (c1 << 16);
       uint32_t p0, p1;
       w3_counter_p_both(slot, p0, p1);
@@ -213,20 +214,73 @@ int hs_decompress_block(const w3_hashtab *tab, const uint8_t *in, size_t n_in, u
 /* the lane decoder (w3_lane.cuh: what every lane of w3_decode_blocks_lane executes), on a copy of
  * the stream placed `misalign` bytes past a word boundary and followed by `junk` (what the next
  * block's stream would be in a packed buffer) */
+struct hs_lane_env {
+  std::vector<w3_lane_tab> lt;
+  std::vector<uint32_t> buf;
+  uint8_t *sp;
+  hs_lane_env(const w3_hashtab *tab, const uint8_t *in, size_t n_in, unsigned misalign, uint8_t junk)
+      : lt(1), buf((n_in + 64) / 4 + 8, 0x01010101u * junk) {
+    for (uint32_t i = 0; i < 8u * W3_LANE_ROW; i++) lt[0].thi31[i] = w3_lane_tab_thi31(tab, i);
+    for (uint32_t i = 0; i < 8u * W3_LANE_NCELL; i++) lt[0].cellb[i] = w3_lane_tab_cellb(tab, i);
+    sp = reinterpret_cast<uint8_t *>(buf.data()) + 4 + (misalign & 3u);
+    memcpy(sp, in, n_in);
+  }
+  w3_lane_mem mem(uint32_t *cnt, const w3_hashtab *tab) {
+    w3_lane_mem m;
+    m.thi31 = (w3_sptr)lt[0].thi31;
+    m.cellb = (w3_sptr)lt[0].cellb;
+    m.cnt = (w3_sptr)cnt;
+    m.g = tab;
+    m.ones = 0xFFFFFFFFu;
+    return m;
+  }
+};
 int hs_lane_decode_block(const w3_hashtab *tab, const uint8_t *in, size_t n_in, unsigned misalign,
                          uint8_t junk, uint8_t *out, size_t n_out) {
-  std::vector<w3_lane_tab> lt(1);
-  for (uint32_t i = 0; i < 8u * W3_LANE_ROW; i++) lt[0].thi[i] = w3_lane_tab_thi(tab, i);
-  for (uint32_t i = 0; i < 8u * W3_LANE_NCELL; i++) lt[0].cellb[i] = w3_lane_tab_cellb(tab, i);
-  std::vector<uint32_t> buf((n_in + 64) / 4 + 8, 0x01010101u * junk);
-  uint8_t *sp = reinterpret_cast<uint8_t *>(buf.data()) + 4 + (misalign & 3u);
-  memcpy(sp, in, n_in);
+  hs_lane_env env(tab, in, n_in, misalign, junk);
   std::vector<uint32_t> cnt(W3_NCTX, 0u);
   std::vector<uint32_t> dst((n_out + 3) / 4 + 1, 0u);
-  w3_lane_decode_block(sp, (uint32_t)n_in, (uint32_t)n_out, reinterpret_cast<uint8_t *>(dst.data()), cnt.data(),
-                       lt.data(), tab, 0xFFFFFFFFu);
+  w3_lane_decode_block(env.sp, (uint32_t)n_in, (uint32_t)n_out, reinterpret_cast<uint8_t *>(dst.data()),
+                       env.mem(cnt.data(), tab));
   memcpy(out, dst.data(), n_out);
   return 0;
+}
+
+/* the pair form of the lane decoder: both lanes of a pair in lockstep, the pick (a shuffle on the
+ * device) done by hand.  Each lane applies the (identical) counter update, as on the device; so
+ * that lane 1's does not see lane 0's, each has its own copy, and they must stay equal. */
+int hs_pair_decode_block(const w3_hashtab *tab, const uint8_t *in, size_t n_in, unsigned misalign,
+                         uint8_t junk, uint8_t *out, size_t n_out) {
+  hs_lane_env env(tab, in, n_in, misalign, junk);
+  const uint32_t sh = (uint32_t)((uintptr_t)env.sp & 3u);
+  const uint32_t *ab = (const uint32_t *)(env.sp - sh);
+  const uint32_t bp0 = sh * 8u, end_bits = bp0 + (uint32_t)n_in * 8u;
+  std::vector<uint32_t> cnt0(W3_NCTX, 0u), cnt1(W3_NCTX, 0u);
+  const w3_lane_mem m[2] = {env.mem(cnt0.data(), tab), env.mem(cnt1.data(), tab)};
+  w3_pair_dec s[2];
+  for (uint32_t g = 0; g < 2; g++) {
+    w3_pair_init(s[g], ab, bp0, end_bits);
+    w3_pair_back(s[g], g, 1u, m[g]);
+  }
+  for (size_t i = 0; i < n_out; i++) {
+    uint32_t byte = 0;
+    const bool fast = s[0].c.bp + W3_LANE_FAST_MARGIN <= end_bits;
+    for (uint32_t a = 0; a < 8u; a++) {
+      uint32_t bit[2];
+      for (uint32_t g = 0; g < 2; g++)
+        bit[g] = fast ? w3_pair_front<false>(s[g], m[g], ab, end_bits) : w3_pair_front<true>(s[g], m[g], ab, end_bits);
+      if (bit[0] != bit[1]) return -1;
+      const uint32_t ci = s[bit[0]].cci, P = s[bit[0]].cP;
+      for (uint32_t g = 0; g < 2; g++) {
+        s[g].ci = ci;
+        s[g].P = P;
+        w3_pair_back(s[g], g, (a + 2u) & 7u, m[g]);
+      }
+      byte = (byte << 1) | bit[0];
+    }
+    out[i] = (uint8_t)byte;
+  }
+  return cnt0 == cnt1 ? 0 : -2;
 }
 
 /* ---- w3_tierb.cuh on the CPU -------------------------------------------------------------- */

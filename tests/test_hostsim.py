@@ -201,34 +201,37 @@ def test_fixed_latency_rank_lookup(libs):
 # ---- the lane decoder (w3_lane.cuh), on the CPU ------------------------------------------------
 
 
+@pytest.mark.parametrize("pair", [False, True], ids=["lane", "pair"])
 @pytest.mark.parametrize("n", [0, 1, 2, 3, 4, 5, 31, 100, 4097, 70001])
-def test_lane_decoder_equals_oracle(libs, n):
-    """The statements every lane of w3_decode_blocks_lane executes, at every start
+def test_lane_decoder_equals_oracle(libs, n, pair):
+    """The statements every lane of w3_decode_blocks_lane / _pair executes, at every start
     misalignment of a packed stream and with the next stream's bytes right behind it."""
     data = w3_corpus.generate(n, offset=4242)
     stream = libs.oracle.compress_block(data)
     for mis in range(4):
-        assert libs.hostsim.lane_decode_block(stream, n, mis) == data, (n, mis)
-        assert libs.hostsim.lane_decode_block(stream, n, mis, junk=0xFF) == data, (n, mis)
+        assert libs.hostsim.lane_decode_block(stream, n, mis, pair=pair) == data, (n, mis)
+        assert libs.hostsim.lane_decode_block(stream, n, mis, junk=0xFF, pair=pair) == data, (n, mis)
 
 
-def test_lane_decoder_hostile_and_truncated(libs):
+@pytest.mark.parametrize("pair", [False, True], ids=["lane", "pair"])
+def test_lane_decoder_hostile_and_truncated(libs, pair):
     rnd = random.Random(17)
     cases = [bytes(rnd.getrandbits(8) for _ in range(20000)), bytes(30000), b"\xff" * 30000,
              b"e" * 70000, bytes(range(256)) * 40, b"\x80" * 5000 + b"\x01" * 5000]
     for data in cases:
         stream = libs.oracle.compress_block(data)
-        assert libs.hostsim.lane_decode_block(stream, len(data), 1) == data
+        assert libs.hostsim.lane_decode_block(stream, len(data), 1, pair=pair) == data
     # a cut stream decodes with zero bits past its end, exactly as ACReader does (io.rs:23-25)
     data = w3_corpus.generate(6000)
     stream = libs.oracle.compress_block(data)
     for cut in (0, 1, 3, 4, 5, len(stream) // 2, len(stream) - 1):
         want = libs.oracle.decompress_block(stream[:cut], len(data))
         for mis in (0, 3):
-            assert libs.hostsim.lane_decode_block(stream[:cut], len(data), mis) == want, cut
+            assert libs.hostsim.lane_decode_block(stream[:cut], len(data), mis, pair=pair) == want, cut
 
 
-def test_lane_decoder_keys_on_thresholds(libs):
+@pytest.mark.parametrize("pair", [False, True], ids=["lane", "pair"])
+def test_lane_decoder_keys_on_thresholds(libs, pair):
     """Histories that put the key exactly on a threshold (singular keys: general search) in the stream."""
     thr, _ = libs.hostsim.thresholds()
     rnd = random.Random(5)
@@ -240,4 +243,4 @@ def test_lane_decoder_keys_on_thresholds(libs):
             chunks.append(bits.to_bytes(8, "big"))
     data = b"".join(chunks)
     stream = libs.oracle.compress_block(data)
-    assert libs.hostsim.lane_decode_block(stream, len(data), 2) == data
+    assert libs.hostsim.lane_decode_block(stream, len(data), 2, pair=pair) == data

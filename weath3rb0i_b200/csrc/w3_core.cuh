@@ -322,6 +322,18 @@ W3_HD float w3_rcp_of(uint32_t d) {
   return 1.0f / (float)d;
 #endif
 }
+/* Counter::p with ONE correction each way: the float estimate of the quotient q <= 131068 carries
+ * a relative error of a few 2^-23 (two roundings and rcp.approx), i.e. at most 0.05 absolute, so
+ * its floor is within one of the true floor.  Ten instructions fewer than w3_counter_p; the device
+ * self-test (w3_selftest_counter_p) checks all 65535^2 count pairs against the u64 statement. */
+W3_HD uint32_t w3_counter_p1(uint32_t c0, uint32_t c1) {
+  const uint32_t a = c1 + 1u, d = c0 + c1 + 2u;
+  uint32_t q = (uint32_t)((float)a * (w3_rcp_of(d) * 131072.0f));
+  const int32_t rem = (int32_t)((a << 17) - q * d);
+  q = q - ((uint32_t)rem >> 31) + (rem >= (int32_t)d ? 1u : 0u);
+  return (q >> 1) + (q & 1u);
+}
+
 /* Counter::p after Counter::update with a 0 and with a 1, from the counter as it
  * stands (slot = c0 | c1 << 16): what the decode speculators prepare for every
  * guessed context.  Unless the update halves (counter.rs:22-25; then the general

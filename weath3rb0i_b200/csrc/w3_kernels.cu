@@ -523,6 +523,7 @@ __global__ void w3_k_counter_p_check(unsigned long long *mismatches) {
   unsigned long long bad = 0;
   for (uint32_t c1 = threadIdx.x; c1 <= 65534u; c1 += blockDim.x) {
     bad += w3_counter_p(c0, c1) != w3_counter_p_u64(c0, c1);
+    bad += w3_counter_p1(c0, c1) != w3_counter_p_u64(c0, c1); /* the lane decoder's single-correction form */
     /* the speculators' pair form: both updates of this state */
     const uint32_t slot = c0 | (c1 << 16);
     uint32_t p0, p1;
@@ -639,6 +640,7 @@ static inline uint32_t w3_per_cta(uint32_t n_blocks, int sm_count, uint32_t cap)
 }
 
 #define W3_LANE_SMEM_MAX (227u * 1024u)
+#define W3_PAIR_MAX_Q 12u /* blocks per SM up to which the pair form of the lane decoder is chosen */
 static inline uint32_t w3_lane_cap(void) { return (W3_LANE_SMEM_MAX - (uint32_t)sizeof(w3_lane_tab)) / (W3_NCTX * 4u); }
 
 extern "C" {
@@ -665,6 +667,9 @@ cudaError_t w3_kernels_init(void) {
                            (int)(sizeof(w3_dec_tab) + sizeof(w3_dec_team)));
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(w3_decode_blocks_lane, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(sizeof(w3_lane_tab) + w3_lane_cap() * W3_NCTX * 4u));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(w3_decode_blocks_pair, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)(sizeof(w3_lane_tab) + w3_lane_cap() * W3_NCTX * 4u));
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(w3_k_hash_array, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -734,18 +739,27 @@ cudaError_t w3_launch_decode(const uint8_t *d_comp, const uint64_t *d_offsets, u
     return cudaGetLastError();
   }
   /* lane per block: `resident` blocks per CTA at a time, spread over `warps` warps (one per SM
-   * sub-partition by default) of `lanes` active lanes */
+   * sub-partition by default) of `lanes` blocks each.  Up to W3_PAIR_MAX_Q blocks per SM the chain
+   * of a block, not instruction issue, sets the pace: the pair form (two lanes per block, the next
+   * position's lookup overlapping the current bit's coder step) is used. */
   const uint32_t per = w3_per_cta(n_blocks, sm_count, w3_lane_cap());
   uint32_t warps = per < 4u ? per : 4u;
   if (opts && opts->lane_warps > 0) warps = (uint32_t)opts->lane_warps < W3_LANE_MAX_WARPS ? (uint32_t)opts->lane_warps : W3_LANE_MAX_WARPS;
   if (warps > per) warps = per;
   uint32_t lanes = w3_ceil_div(per, warps);
   while (warps * lanes > w3_lane_cap()) lanes--; /* rounding up may overshoot what fits */
+  const uint32_t q = w3_ceil_div(n_blocks, (uint32_t)sm_count);
+  bool pair = q <= W3_PAIR_MAX_Q;
+  if (opts && opts->lane_form) pair = opts->lane_form == 2;
+  if (pair && lanes > 16u) lanes = 16u;
   const uint32_t resident = warps * lanes;
   uint32_t grid = w3_ceil_div(n_blocks, resident);
   if (grid > (uint32_t)sm_count) grid = (uint32_t)sm_count;
-  w3_decode_blocks_lane<<<grid, warps * 32u, sizeof(w3_lane_tab) + (size_t)resident * W3_NCTX * 4u, s>>>(
-      d_comp, d_offsets, n_blocks, block_size, n_total, d_out, d_err, d_tab, lanes);
+  const size_t smem = sizeof(w3_lane_tab) + (size_t)resident * W3_NCTX * 4u;
+  if (pair)
+    w3_decode_blocks_pair<<<grid, warps * 32u, smem, s>>>(d_comp, d_offsets, n_blocks, block_size, n_total, d_out, d_err, d_tab, lanes);
+  else
+    w3_decode_blocks_lane<<<grid, warps * 32u, smem, s>>>(d_comp, d_offsets, n_blocks, block_size, n_total, d_out, d_err, d_tab, lanes);
   return cudaGetLastError();
 }
 

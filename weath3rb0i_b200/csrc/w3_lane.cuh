@@ -1,5 +1,6 @@
 /*
- * w3_lane.cuh — "lane" decode: one LANE per block, for the many-block regime
+ * w3_lane.cuh — "lane" decode for the many-block regime: a block is decoded by
+ * one lane (or a pair of lanes) of a warp instead of a whole warp or CTA
  * (1 GiB in 1 MiB blocks on one GPU is 7 blocks per SM; 256 KiB blocks, 28).
  *
  * decompress() of the reference (src/main.rs:131-140) is one dependent chain
@@ -9,10 +10,23 @@
  * 678 cycles per bit at 7 blocks per SM, profiles/r01_1gib_*).  The integer
  * pipes of an SM sub-partition retire one warp-instruction per two cycles
  * whatever the number of active lanes, so the instruction, not the lane, is
- * the unit of cost: here every lane runs its own block, and one instruction
- * stream decodes up to 32 blocks at once.  Lanes never talk to each other, so
- * the per-lane code is plain sequential code — `__host__ __device__`, and
- * tests/hostsim runs exactly these statements against the oracle on the CPU.
+ * the unit of cost: here every lane (pair) runs its own block, and one
+ * instruction stream decodes up to 32 (16) blocks at once.
+ *
+ *   lane form   one lane per block; lanes never talk to each other.  Chosen
+ *               when there are so many blocks per SM that shared memory
+ *               (8 KiB of counters per resident block) is what limits.
+ *   pair form   two lanes per block.  Both run the coder step on the same
+ *               values; lane g additionally prepares context and probability
+ *               of the NEXT position for the case that the bit being decoded
+ *               is g, so the table lookup and Counter::p overlap the coder
+ *               arithmetic instead of following it; one shuffle pair picks the
+ *               survivor.  Chosen while the chain of a block, not issue, sets
+ *               the pace (few blocks per SM).
+ *
+ * The per-lane code is plain sequential code — `__host__ __device__` — and
+ * tests/hostsim runs exactly these statements against the oracle on the CPU
+ * (the pair form with both lanes in lockstep and the pick done by hand).
  *
  * Shared memory of a CTA: one copy of the lookup tables (w3_lane_tab, 72 KiB)
  * and 8 KiB of counters per resident block (Counter — src/models/counter.rs;
@@ -23,56 +37,103 @@
  * The entropy hash (ACHistory::hash — src/history/ac_history.rs:28-46) is the
  * rank of the bit-reversed history among <= 255 thresholds per alignment
  * (w3_core.cuh).  Lookup: a byte per (alignment, top 13 key bits) gives the
- * number of thresholds below the key's cell; the next W3_LANE_FIX thresholds'
- * high words are loaded at once and compared (thresholds ascend, so those past
- * the cell compare greater by themselves).  A tie on a high word, or all
- * W3_LANE_FIX compares true, sends that lane through the general search
- * (w3_rank_lookup, w3_achash_exact) over the tables in global memory.
+ * number of thresholds below the key's cell; the next W3_LANE_FIX thresholds
+ * are loaded at once and compared on the top 31 bits of their high words by
+ * subtraction (the sign bits add up to the rank; thresholds ascend, so those
+ * past the cell compare greater by themselves).  A tie on those 31 bits, or
+ * all W3_LANE_FIX thresholds below the key, sends that lane through the
+ * general search (w3_rank_lookup, w3_achash_exact) over the tables in global
+ * memory: about one lookup in a hundred on text.
  */
 #pragma once
 #include "w3_core.cuh"
 
 #define W3_LANE_PB W3_PB2
 #define W3_LANE_NCELL (1u << W3_LANE_PB)
-#define W3_LANE_FIX 6
-#define W3_LANE_ROW 264u /* 255 thresholds + ~0 padding: a lookup reads W3_LANE_FIX entries from any base <= 255 */
+#ifndef W3_LANE_FIX
+#define W3_LANE_FIX 4
+#endif
+#define W3_LANE_ROW 264u /* 255 thresholds + padding: a lookup reads W3_LANE_FIX entries from any base <= 255 */
 static_assert(255u + W3_LANE_FIX <= W3_LANE_ROW, "threshold rows must cover the read-ahead");
 
 struct w3_lane_tab {
-  uint32_t thi[8 * W3_LANE_ROW];    /* high words of thr[a][j] */
+  uint32_t thi31[8 * W3_LANE_ROW];  /* thr[a][j] >> 33: the top 31 bits; padding 0x7FFFFFFF */
   uint8_t cellb[8 * W3_LANE_NCELL]; /* #{j : thr[a][j] < first key of the cell} */
+  uint32_t ones;                    /* 0xFFFFFFFF, read back into a register ptxas cannot fold */
+  uint32_t pad[3];
 };
 static_assert(sizeof(w3_lane_tab) % 16 == 0, "counters follow the tables at 16-byte alignment");
 
 /* entry i of the staged tables, from the context's table in global memory */
-W3_HD uint32_t w3_lane_tab_thi(const w3_hashtab *g, uint32_t i) {
+W3_HD uint32_t w3_lane_tab_thi31(const w3_hashtab *g, uint32_t i) {
   const uint32_t a = i / W3_LANE_ROW, j = i % W3_LANE_ROW;
-  return j < 255u ? (uint32_t)(g->thr[a][j] >> 32) : 0xFFFFFFFFu;
+  return j < 255u ? (uint32_t)(g->thr[a][j] >> 33) : 0x7FFFFFFFu;
 }
 W3_HD uint8_t w3_lane_tab_cellb(const w3_hashtab *g, uint32_t i) {
   return (uint8_t)(g->cell2[i / W3_LANE_NCELL][i % W3_LANE_NCELL] & 0xFFu);
 }
 
-/* rank of a key among the thresholds of alignment a, from the key's high word */
-W3_HD uint32_t w3_lane_rank(uint32_t khi, uint32_t a, const uint32_t *thi, const uint8_t *cellb, bool &bad) {
-  const uint32_t base = cellb[a * W3_LANE_NCELL + (khi >> (32u - W3_LANE_PB))];
-  const uint32_t *t = thi + a * W3_LANE_ROW + base;
+/* ---- shared-memory accessors ------------------------------------------------
+ * On the device a block's counters and the tables are addressed by 32-bit
+ * shared-window addresses held in registers: left to generic pointers the
+ * compiler re-derives the window base (S2UR SR_CgaCtaId, ULEA) inside the
+ * unrolled loop.  On the host the same type is a plain address. */
+#if defined(__CUDA_ARCH__)
+typedef uint32_t w3_sptr;
+W3_HD uint32_t w3_s_ld32c(w3_sptr a) { /* constant tables: schedulable */
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+W3_HD uint32_t w3_s_ld8c(w3_sptr a) {
+  uint32_t v;
+  asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+W3_HD uint32_t w3_s_ld32(w3_sptr a) { /* counters: volatile asm statements keep their order */
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+W3_HD void w3_s_st32(w3_sptr a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
+#else
+typedef uintptr_t w3_sptr;
+W3_HD uint32_t w3_s_ld32c(w3_sptr a) { return *(const uint32_t *)a; }
+W3_HD uint32_t w3_s_ld8c(w3_sptr a) { return *(const uint8_t *)a; }
+W3_HD uint32_t w3_s_ld32(w3_sptr a) { return *(const uint32_t *)a; }
+W3_HD void w3_s_st32(w3_sptr a, uint32_t v) { *(uint32_t *)a = v; }
+#endif
+/* what a lane needs of its CTA's shared memory */
+struct w3_lane_mem {
+  w3_sptr thi31, cellb; /* w3_lane_tab */
+  w3_sptr cnt;          /* this block's 2048 counters */
+  const w3_hashtab *g;  /* the full tables in global memory (general search) */
+  uint32_t ones;
+};
+
+/* rank of a key among the thresholds of alignment a, from the top 31 bits of the key */
+W3_HD uint32_t w3_lane_rank(uint32_t khi, uint32_t a, const w3_lane_mem &m, bool &bad) {
+  const uint32_t base = w3_s_ld8c(m.cellb + a * W3_LANE_NCELL + (khi >> (32u - W3_LANE_PB)));
+  const w3_sptr t = m.thi31 + (a * W3_LANE_ROW + base) * 4u;
   uint32_t b[W3_LANE_FIX];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-  for (int i = 0; i < W3_LANE_FIX; i++) b[i] = t[i];
-  uint32_t r = base;
+  for (int i = 0; i < W3_LANE_FIX; i++) b[i] = w3_s_ld32c(t + 4u * (uint32_t)i);
+  /* z = key31 - threshold31 fits a signed word: > 0 the threshold is below the key, < 0 above, 0 undecided */
+  const uint32_t k31 = khi >> 1;
+  uint32_t above = 0;
   bool tie = false;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int i = 0; i < W3_LANE_FIX; i++) {
-    r += khi > b[i] ? 1u : 0u;
-    tie |= khi == b[i];
+    const uint32_t z = k31 - b[i];
+    above += z >> 31;
+    tie |= z == 0u;
   }
-  bad = tie || khi > b[W3_LANE_FIX - 1]; /* all compares true: there may be more thresholds below the key */
-  return r;
+  bad = tie || above == 0u; /* none above: there may be more thresholds below the key than were looked at */
+  return base + (uint32_t)W3_LANE_FIX - above;
 }
 /* the general search, for the lane the fixed lookup declined (rare) */
 #if defined(__CUDACC__)
@@ -115,75 +176,86 @@ W3_HD uint32_t w3_lane_fresh(const uint32_t *ab, uint32_t bp, uint32_t end_bits)
   return w3_fsl(w1, w0, bp);
 }
 
-struct w3_lane_dec {
+/* the coder's half of a decode step: narrow by the bit, both renormalisation loops in closed
+ * form (arithmetic_coder.rs:85-102; of the E3 flips of x only the last survives the shifts) */
+struct w3_lane_coder {
   uint32_t x1, x2, x; /* ArithmeticCoder — arithmetic_coder.rs:11-18 */
   uint32_t bp;        /* stream bits consumed, counted from the aligned base */
-  uint32_t khi, klo;  /* ACHistory.bits, newest bit at bit 63 (w3_key_of_history) */
-  uint32_t ci;        /* counter of the current context: (rank << 3) | alignment */
 };
-
-/* one pass of the decompress loop (main.rs:134-137) for the bit whose successor
- * has alignment a1; cnt = this block's 2048 counters */
 template <bool kCareful>
-W3_HD uint32_t w3_lane_dec_step(w3_lane_dec &s, uint32_t a1, uint32_t *cnt, const w3_lane_tab *lt,
-                                const w3_hashtab *g, const uint32_t *ab, uint32_t end_bits, uint32_t ones) {
-  const uint32_t c = cnt[s.ci];
-  const uint32_t P = w3_counter_p(c & 0xFFFFu, c >> 16) << 16;  /* predict — main.rs:134 */
-  const uint32_t m = w3_umulhi(s.x2 - s.x1, P);                 /* lerp — arithmetic_coder.rs:81 */
-  const uint32_t bit = (s.x - s.x1) <= m ? 1u : 0u;             /* :82; x >= x1 always */
-  if (bit) s.x2 = s.x1 + m;                                     /* :85-88 */
-  else s.x1 = s.x1 + m + 1u;
-  cnt[s.ci] = w3_counter_update(c, bit);                        /* adapt — main.rs:136, ordern_entropy.rs:32-34 */
-  s.klo = w3_fsr(s.klo, s.khi, 1u);                             /* history — ac_history.rs:23-26 */
-  s.khi = (s.khi >> 1) | (bit << 31);
-  bool bad;
-  uint32_t r = w3_lane_rank(s.khi, a1, lt->thi, lt->cellb, bad); /* hash — ordern_entropy.rs:36-45 */
-  if (bad) r = w3_lane_rank_slow(s.khi, s.klo, a1, g);
-  s.ci = (r << W3_ALIGN_BITS) | a1;
-  /* both renormalisation loops (:91-102) in closed form; of the E3 flips of x only the last survives */
-  const uint32_t fresh = w3_lane_fresh<kCareful>(ab, s.bp, end_bits);
+W3_HD uint32_t w3_lane_coder_step(w3_lane_coder &c, uint32_t P, const uint32_t *ab, uint32_t end_bits, uint32_t ones) {
+  const uint32_t m = w3_umulhi(c.x2 - c.x1, P);         /* lerp — arithmetic_coder.rs:81 */
+  const uint32_t bit = (c.x - c.x1) <= m ? 1u : 0u;     /* :82; x >= x1 always */
+  if (bit) c.x2 = c.x1 + m;                             /* :85-88 */
+  else c.x1 = c.x1 + m + 1u;
+  const uint32_t fresh = w3_lane_fresh<kCareful>(ab, c.bp, end_bits);
   int sh_s, sh_k;
-  const int n = w3_ac_renorm_ones(s.x1, s.x2, sh_s, sh_k, ones);
-  s.x = w3_fsl(fresh, s.x, (uint32_t)n) ^ ((0u - (uint32_t)sh_k) & 0x80000000u);
-  s.bp += (uint32_t)n;
+  const int n = w3_ac_renorm_ones(c.x1, c.x2, sh_s, sh_k, ones);
+  c.x = w3_fsl(fresh, c.x, (uint32_t)n) ^ ((0u - (uint32_t)sh_k) & 0x80000000u);
+  c.bp += (uint32_t)n;
   if (kCareful) { /* everything from end_bits on reads as zero: keep bp from running away on a cut stream */
     const uint32_t cap = end_bits + 64u;
-    s.bp = s.bp < cap ? s.bp : cap;
+    c.bp = c.bp < cap ? c.bp : cap;
   }
   return bit;
 }
+W3_HD void w3_lane_coder_init(w3_lane_coder &c, const uint32_t *ab, uint32_t bp0, uint32_t end_bits) {
+  c.x1 = 0u;
+  c.x2 = 0xFFFFFFFFu;
+  c.x = w3_lane_fresh<true>(ab, bp0, end_bits); /* new_decoder — arithmetic_coder.rs:75-78 */
+  c.bp = bp0 + 32u;
+}
+
+/* Counter::p << 16 of a counter word (c0 | c1 << 16) */
+W3_HD uint32_t w3_lane_P(uint32_t c) { return w3_counter_p1(c & 0xFFFFu, c >> 16) << 16; }
 
 /* stream bits the eight steps of one byte can consume at most, plus the two words a step looks at */
 #define W3_LANE_FAST_MARGIN (8u * 31u + 64u)
 
+/* ---- lane form --------------------------------------------------------------- */
+struct w3_lane_dec {
+  w3_lane_coder c;
+  uint32_t khi, klo; /* ACHistory.bits, newest bit at bit 63 (w3_key_of_history) */
+  uint32_t ci;       /* byte offset of the current context's counter: ((rank << 3) | alignment) * 4 */
+};
+
+/* one pass of the decompress loop (main.rs:134-137) for the bit whose successor has alignment a1 */
+template <bool kCareful>
+W3_HD uint32_t w3_lane_dec_step(w3_lane_dec &s, uint32_t a1, const w3_lane_mem &m, const uint32_t *ab, uint32_t end_bits) {
+  const uint32_t cw = w3_s_ld32(m.cnt + s.ci);
+  const uint32_t bit = w3_lane_coder_step<kCareful>(s.c, w3_lane_P(cw), ab, end_bits, m.ones); /* predict + decode — main.rs:134-135 */
+  w3_s_st32(m.cnt + s.ci, w3_counter_update(cw, bit)); /* adapt — main.rs:136, ordern_entropy.rs:32-34 */
+  s.klo = w3_fsr(s.klo, s.khi, 1u);                    /* history — ac_history.rs:23-26 */
+  s.khi = (s.khi >> 1) | (bit << 31);
+  bool bad;
+  uint32_t r = w3_lane_rank(s.khi, a1, m, bad);        /* hash — ordern_entropy.rs:36-45 */
+  if (bad) r = w3_lane_rank_slow(s.khi, s.klo, a1, m.g);
+  s.ci = ((r << W3_ALIGN_BITS) | a1) * 4u;
+  return bit;
+}
+
 /* decompress one block: stream sp[0..slen) -> dst[0..n).  slen * 8 + 1024 must fit in 32 bits. */
-W3_HD void w3_lane_decode_block(const uint8_t *sp, uint32_t slen, uint32_t n, uint8_t *dst, uint32_t *cnt,
-                                const w3_lane_tab *lt, const w3_hashtab *g, uint32_t ones) {
+W3_HD void w3_lane_decode_block(const uint8_t *sp, uint32_t slen, uint32_t n, uint8_t *dst, const w3_lane_mem &m) {
   const uint32_t sh = (uint32_t)((uintptr_t)sp & 3u);
   const uint32_t *ab = (const uint32_t *)(sp - sh);
   const uint32_t bp0 = sh * 8u, end_bits = bp0 + slen * 8u;
   w3_lane_dec s;
-  s.x1 = 0u;
-  s.x2 = 0xFFFFFFFFu;
-  s.x = w3_lane_fresh<true>(ab, bp0, end_bits); /* new_decoder — arithmetic_coder.rs:75-78 */
-  s.bp = bp0 + 32u;
+  w3_lane_coder_init(s.c, ab, bp0, end_bits);
   s.khi = s.klo = 0u;
-  s.ci = W3_CTX0_RANKED;
+  s.ci = W3_CTX0_RANKED * 4u;
   uint32_t word = 0;
   for (uint32_t i = 0; i < n; i++) {
     uint32_t byte = 0;
-    if (s.bp + W3_LANE_FAST_MARGIN <= end_bits) {
+    if (s.c.bp + W3_LANE_FAST_MARGIN <= end_bits) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-      for (uint32_t a = 0; a < 8u; a++)
-        byte = (byte << 1) | w3_lane_dec_step<false>(s, (a + 1u) & 7u, cnt, lt, g, ab, end_bits, ones);
+      for (uint32_t a = 0; a < 8u; a++) byte = (byte << 1) | w3_lane_dec_step<false>(s, (a + 1u) & 7u, m, ab, end_bits);
     } else {
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-      for (uint32_t a = 0; a < 8u; a++)
-        byte = (byte << 1) | w3_lane_dec_step<true>(s, (a + 1u) & 7u, cnt, lt, g, ab, end_bits, ones);
+      for (uint32_t a = 0; a < 8u; a++) byte = (byte << 1) | w3_lane_dec_step<true>(s, (a + 1u) & 7u, m, ab, end_bits);
     }
     word |= byte << (8u * (i & 3u));
     if ((i & 3u) == 3u) {
@@ -194,12 +266,64 @@ W3_HD void w3_lane_decode_block(const uint8_t *sp, uint32_t slen, uint32_t n, ui
   for (uint32_t b = 0; b < (n & 3u); b++) dst[(n & ~3u) + b] = (uint8_t)(word >> (8u * b));
 }
 
+/* ---- pair form ----------------------------------------------------------------
+ * Contexts of consecutive positions differ in their alignment bits, so a
+ * candidate never reads a counter that the update in flight touches.  Written
+ * as two halves around the pick so that tests/hostsim can run both lanes in
+ * lockstep on the CPU. */
+struct w3_pair_dec {
+  w3_lane_coder c;
+  uint32_t khi, klo;
+  uint32_t ci, P;   /* counter offset and Counter::p << 16 of the bit being decoded (both lanes agree) */
+  uint32_t cci, cP; /* this lane's candidate for the next position: valid if the current bit equals its guess */
+};
+
+/* this lane's candidate for the position of alignment a2, assuming the next bit to be decoded is g */
+W3_HD void w3_pair_back(w3_pair_dec &s, uint32_t g, uint32_t a2, const w3_lane_mem &m) {
+  const uint32_t gk = (s.khi >> 1) | (g << 31);
+  bool bad;
+  uint32_t r = w3_lane_rank(gk, a2, m, bad);
+  if (bad) r = w3_lane_rank_slow(gk, w3_fsr(s.klo, s.khi, 1u), a2, m.g);
+  s.cci = ((r << W3_ALIGN_BITS) | a2) * 4u;
+  s.cP = w3_lane_P(w3_s_ld32(m.cnt + s.cci));
+}
+/* decode the current bit (main.rs:134-137 without the hash), both lanes alike */
+template <bool kCareful>
+W3_HD uint32_t w3_pair_front(w3_pair_dec &s, const w3_lane_mem &m, const uint32_t *ab, uint32_t end_bits) {
+  const uint32_t bit = w3_lane_coder_step<kCareful>(s.c, s.P, ab, end_bits, m.ones);
+  w3_s_st32(m.cnt + s.ci, w3_counter_update(w3_s_ld32(m.cnt + s.ci), bit)); /* both lanes store the same word */
+  s.klo = w3_fsr(s.klo, s.khi, 1u);
+  s.khi = (s.khi >> 1) | (bit << 31);
+  return bit;
+}
+W3_HD void w3_pair_init(w3_pair_dec &s, const uint32_t *ab, uint32_t bp0, uint32_t end_bits) {
+  w3_lane_coder_init(s.c, ab, bp0, end_bits);
+  s.khi = s.klo = 0u;
+  s.ci = W3_CTX0_RANKED * 4u;
+  s.P = 0x80000000u; /* Counter::new: p = 32768 */
+}
+
 #if defined(__CUDACC__)
 /* ------------------------------------------------------------------------ */
-/* the kernel: blockDim.x / 32 warps of `lanes` active lanes; a CTA decodes   */
-/* warps * lanes blocks per round                                             */
+/* kernels: blockDim.x / 32 warps; a CTA decodes warps * lanes blocks per     */
+/* round (lanes = blocks per warp)                                            */
 
 #define W3_LANE_MAX_WARPS 8u
+
+__device__ __forceinline__ void w3_lane_stage(w3_lane_tab *lt, const w3_hashtab *tab) {
+  for (uint32_t i = threadIdx.x; i < 8u * W3_LANE_ROW; i += blockDim.x) lt->thi31[i] = w3_lane_tab_thi31(tab, i);
+  for (uint32_t i = threadIdx.x; i < 8u * W3_LANE_NCELL; i += blockDim.x) lt->cellb[i] = w3_lane_tab_cellb(tab, i);
+  if (threadIdx.x == 0) lt->ones = 0xFFFFFFFFu;
+}
+__device__ __forceinline__ w3_lane_mem w3_lane_mem_of(w3_lane_tab *lt, uint32_t *cnt, const w3_hashtab *tab) {
+  w3_lane_mem m;
+  m.thi31 = (w3_sptr)__cvta_generic_to_shared(lt->thi31);
+  m.cellb = (w3_sptr)__cvta_generic_to_shared(lt->cellb);
+  m.cnt = (w3_sptr)__cvta_generic_to_shared(cnt);
+  m.g = tab;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(m.ones) : "r"((uint32_t)__cvta_generic_to_shared(&lt->ones)));
+  return m;
+}
 
 __global__ void __launch_bounds__(W3_LANE_MAX_WARPS * 32u)
 w3_decode_blocks_lane(const uint8_t *__restrict__ comp, const uint64_t *__restrict__ offsets, uint32_t n_blocks,
@@ -212,11 +336,7 @@ w3_decode_blocks_lane(const uint8_t *__restrict__ comp, const uint64_t *__restri
   const uint32_t per_cta = (blockDim.x >> 5) * lanes;
   const uint32_t slot = warp * lanes + lane;
 
-  for (uint32_t i = threadIdx.x; i < 8u * W3_LANE_ROW; i += blockDim.x) lt->thi[i] = w3_lane_tab_thi(tab, i);
-  for (uint32_t i = threadIdx.x; i < 8u * W3_LANE_NCELL; i += blockDim.x) lt->cellb[i] = w3_lane_tab_cellb(tab, i);
-  uint32_t ones;
-  asm volatile("mov.u32 %0, 0xFFFFFFFF;" : "=r"(ones)); /* opaque: ptxas would fold the constant and spend a move per use */
-
+  w3_lane_stage(lt, tab);
   for (uint32_t first = blockIdx.x * per_cta; first < n_blocks; first += gridDim.x * per_cta) {
     __syncthreads(); /* tables staged / the previous round's lanes are done with their counters */
     for (uint32_t i = threadIdx.x; i < per_cta * W3_NCTX; i += blockDim.x) counts[i] = 0u; /* ordern_entropy.rs:17 */
@@ -226,8 +346,85 @@ w3_decode_blocks_lane(const uint8_t *__restrict__ comp, const uint64_t *__restri
       const uint64_t off = (uint64_t)blk * block_size;
       const uint32_t n = (uint32_t)(n_total - off < block_size ? n_total - off : block_size);
       const uint64_t s0 = offsets[blk], slen = offsets[blk + 1] - s0;
-      if (slen > 0x1FFFFF00ull) atomicOr(err, W3_ERR_ABORT); /* stream bits must fit 32 bits (the launcher checks too) */
-      else w3_lane_decode_block(comp + s0, (uint32_t)slen, n, out + off, counts + slot * W3_NCTX, lt, tab, ones);
+      if (slen > 0x1FFFFF00ull) atomicOr(err, W3_ERR_ABORT); /* stream bits must fit 32 bits (the host checks too) */
+      else w3_lane_decode_block(comp + s0, (uint32_t)slen, n, out + off, w3_lane_mem_of(lt, counts + slot * W3_NCTX, tab));
+    }
+  }
+}
+
+/* Pair form: lanes 2p and 2p+1 of a warp decode block p of the warp together.  The pick is a
+ * full-warp shuffle, so the warp's control flow is kept uniform: every lane runs block_size
+ * bytes' worth of steps; pairs beyond `pairs` and beyond the last block shadow a real pair of
+ * the warp (same values, same stores), a short last block keeps stepping over its exhausted
+ * stream without storing. */
+__global__ void __launch_bounds__(W3_LANE_MAX_WARPS * 32u)
+w3_decode_blocks_pair(const uint8_t *__restrict__ comp, const uint64_t *__restrict__ offsets, uint32_t n_blocks,
+                      uint32_t block_size, uint64_t n_total, uint8_t *__restrict__ out, uint32_t *__restrict__ err,
+                      const w3_hashtab *__restrict__ tab, uint32_t pairs) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  w3_lane_tab *lt = reinterpret_cast<w3_lane_tab *>(smem_raw);
+  uint32_t *counts = reinterpret_cast<uint32_t *>(smem_raw + sizeof(w3_lane_tab));
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const uint32_t per_cta = (blockDim.x >> 5) * pairs;
+  const uint32_t g = lane & 1u;
+
+  w3_lane_stage(lt, tab);
+  for (uint32_t first = blockIdx.x * per_cta; first < n_blocks; first += gridDim.x * per_cta) {
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < per_cta * W3_NCTX; i += blockDim.x) counts[i] = 0u;
+    __syncthreads();
+    const uint32_t wfirst = first + warp * pairs; /* this warp's first block */
+    if (wfirst >= n_blocks) continue;              /* warp-uniform */
+    const uint32_t in_warp = n_blocks - wfirst < pairs ? n_blocks - wfirst : pairs;
+    const uint32_t pair = (lane >> 1) % in_warp;   /* pairs without a block of their own shadow one that has */
+    const bool owner = g == 0u && (lane >> 1) < in_warp;
+    const uint32_t blk = wfirst + pair;
+    const uint64_t off = (uint64_t)blk * block_size;
+    const uint32_t n = (uint32_t)(n_total - off < block_size ? n_total - off : block_size);
+    const uint64_t s0 = offsets[blk];
+    uint64_t slen = offsets[blk + 1] - s0;
+    if (slen > 0x1FFFFF00ull) { atomicOr(err, W3_ERR_ABORT); slen = 0; } /* decodes zeros, flagged */
+    const uint8_t *sp = comp + s0;
+    uint8_t *dst = out + off;
+    const uint32_t sh = (uint32_t)((uintptr_t)sp & 3u);
+    const uint32_t *ab = (const uint32_t *)(sp - sh);
+    const uint32_t bp0 = sh * 8u, end_bits = bp0 + (uint32_t)slen * 8u;
+    const w3_lane_mem m = w3_lane_mem_of(lt, counts + (warp * pairs + pair) * W3_NCTX, tab);
+    w3_pair_dec s;
+    w3_pair_init(s, ab, bp0, end_bits);
+    w3_pair_back(s, g, 1u, m);
+    uint32_t word = 0;
+    const uint32_t n_steps = block_size < n_total ? block_size : (uint32_t)n_total; /* the same for every lane */
+    for (uint32_t i = 0; i < n_steps; i++) {
+      uint32_t byte = 0;
+      if (__all_sync(0xFFFFFFFFu, s.c.bp + W3_LANE_FAST_MARGIN <= end_bits)) {
+#pragma unroll
+        for (uint32_t a = 0; a < 8u; a++) {
+          const uint32_t bit = w3_pair_front<false>(s, m, ab, end_bits);
+          const uint32_t src = (lane & 30u) | bit;
+          s.ci = __shfl_sync(0xFFFFFFFFu, s.cci, src);
+          s.P = __shfl_sync(0xFFFFFFFFu, s.cP, src);
+          w3_pair_back(s, g, (a + 2u) & 7u, m);
+          byte = (byte << 1) | bit;
+        }
+      } else {
+#pragma unroll 1
+        for (uint32_t a = 0; a < 8u; a++) {
+          const uint32_t bit = w3_pair_front<true>(s, m, ab, end_bits);
+          const uint32_t src = (lane & 30u) | bit;
+          s.ci = __shfl_sync(0xFFFFFFFFu, s.cci, src);
+          s.P = __shfl_sync(0xFFFFFFFFu, s.cP, src);
+          w3_pair_back(s, g, (a + 2u) & 7u, m);
+          byte = (byte << 1) | bit;
+        }
+      }
+      word |= byte << (8u * (i & 3u));
+      if ((i & 3u) == 3u) {
+        if (owner && i < n) *(uint32_t *)(dst + (i - 3u)) = word;
+        word = 0;
+      }
+      if (owner && i + 1u == n)
+        for (uint32_t b = 0; b < (n & 3u); b++) dst[(n & ~3u) + b] = (uint8_t)(word >> (8u * b));
     }
   }
 }
