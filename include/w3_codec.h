@@ -99,6 +99,13 @@ int w3_compress(w3_ctx *ctx, const uint8_t *in, size_t n, size_t block_size, uin
 int w3_decompress(w3_ctx *ctx, const uint8_t *in, size_t n_in, uint8_t *out, size_t cap,
                   size_t *out_len);
 
+/* The same for blocks [first_block, first_block + n_blocks) of a stream only: out receives those
+ * blocks' bytes (block i of the range at (i - first_block) * block_size).  The streams of the
+ * range must lie within in[0..n_in); what follows them may be missing.  This is what a process
+ * that holds one shard of a job calls (contiguous block ranges, no exchange). */
+int w3_decompress_blocks(w3_ctx *ctx, const uint8_t *in, size_t n_in, size_t first_block, size_t n_blocks,
+                         uint8_t *out, size_t cap, size_t *out_len);
+
 /* Reads only the header: uncompressed length (main.rs:119-126 reads the same field). */
 int w3_decompressed_size(const uint8_t *in, size_t n_in, size_t *out_len);
 

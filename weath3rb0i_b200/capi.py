@@ -21,7 +21,7 @@ DEFAULT_BLOCK = 1 << 20
 SYMBOLS = (
     "w3_ctx_create", "w3_ctx_destroy", "w3_ctx_device_count", "w3_ctx_set_option", "w3_compress_bound",
     "w3_ctx_set_model", "w3_ctx_get_model", "w3_train_model",
-    "w3_compress", "w3_decompress", "w3_decompressed_size",
+    "w3_compress", "w3_decompress", "w3_decompress_blocks", "w3_decompressed_size",
     "w3_encode_device", "w3_pack_device", "w3_decode_device",
     "w3_selftest_achash", "w3_selftest_counter_p", "w3_probe_sector_gather", "w3_selftest_ac_encode", "w3_selftest_ac_decode",
     "w3_selftest_state_table", "w3_selftest_hashslots",
@@ -65,6 +65,7 @@ def load():
     lib.w3_compress_bound.restype = sz
     lib.w3_compress.argtypes = [vp, u8p, sz, sz, C.c_uint32, u8p, sz, C.POINTER(sz)]
     lib.w3_decompress.argtypes = [vp, u8p, sz, u8p, sz, C.POINTER(sz)]
+    lib.w3_decompress_blocks.argtypes = [vp, u8p, sz, sz, sz, u8p, sz, C.POINTER(sz)]
     lib.w3_decompressed_size.argtypes = [u8p, sz, C.POINTER(sz)]
     lib.w3_encode_device.argtypes = [vp, C.c_int, vp, sz, sz, vp, sz, vp, vp, vp]
     lib.w3_pack_device.argtypes = [vp, C.c_int, vp, sz, vp, sz, vp, vp, vp]
@@ -181,6 +182,17 @@ class Context:
         ol = C.c_size_t()
         check(self.lib.w3_decompress(self.handle, _addr(src), n_in, _addr(dst), cap, C.byref(ol)))
         return ol.value
+
+    def decompress_blocks_into(self, src, n_in: int, first_block: int, n_blocks: int, dst, cap: int) -> int:
+        ol = C.c_size_t()
+        check(self.lib.w3_decompress_blocks(self.handle, _addr(src), n_in, first_block, n_blocks, _addr(dst), cap, C.byref(ol)))
+        return ol.value
+
+    def decompress_blocks(self, blob: bytes, first_block: int, n_blocks: int, block_size: int) -> bytes:
+        cap = max(n_blocks * block_size, 1)
+        out = C.create_string_buffer(cap)
+        n = self.decompress_blocks_into(blob, len(blob), first_block, n_blocks, C.addressof(out), cap)
+        return out.raw[:n]
 
     def decompress(self, blob: bytes) -> bytes:
         n = self.decompressed_size(blob)

@@ -10,6 +10,7 @@
  */
 #include <cuda_runtime.h>
 #include <stdarg.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -484,14 +485,13 @@ int w3_decompressed_size(const uint8_t *in, size_t n_in, size_t *out_len) {
   return W3_E_MAGIC;
 }
 
-int w3_decompress(w3_ctx *ctx, const uint8_t *in, size_t n_in, uint8_t *out, size_t cap,
-                  size_t *out_len) {
-  if (!ctx || !in || !out_len || (!out && cap)) return W3_E_ARG;
+/* decode blocks [B0, B1) of a stream (B1 = SIZE_MAX: all of them) into out; the caller holds ctx->mu */
+static int decode_range(w3_ctx *ctx, const uint8_t *in, size_t n_in, size_t B0, size_t B1, uint8_t *out,
+                        size_t cap, size_t *out_len) {
   size_t n = 0;
   int rc = w3_decompressed_size(in, n_in, &n);
   if (rc != W3_OK) return rc;
-  *out_len = n;
-  std::lock_guard<std::mutex> lock(ctx->mu);
+  const bool whole = B1 == SIZE_MAX;
 
   size_t bs, nb, hdr;
   std::vector<uint64_t> offs; /* nb + 1, relative to the first stream byte */
@@ -509,8 +509,6 @@ int w3_decompress(w3_ctx *ctx, const uint8_t *in, size_t n_in, uint8_t *out, siz
     bs = get_be32(in + 16);
     nb = get_be32(in + 20);
     if (!bs || (bs & 3) || bs > MAX_BLOCK || nb != (n + bs - 1) / bs) return W3_E_FORMAT;
-    for (size_t i = 0; i < nb && HDR_BLOCKS + (in[4] == 2 ? HDR_MODEL : 0) + 4 * (i + 1) <= n_in; i++)
-      if (get_be32(in + HDR_BLOCKS + (in[4] == 2 ? HDR_MODEL : 0) + 4 * i) > MAX_STREAM) return W3_E_FORMAT;
     const size_t fixed = HDR_BLOCKS + (in[4] == 2 ? HDR_MODEL : 0);
     hdr = fixed + 4 * nb;
     if (n_in < hdr) return W3_E_FORMAT;
@@ -521,17 +519,29 @@ int w3_decompress(w3_ctx *ctx, const uint8_t *in, size_t n_in, uint8_t *out, siz
     if ((rc = ctx_set_model(ctx, table)) != W3_OK) return rc;
     offs.resize(nb + 1);
     uint64_t run = 0;
-    for (size_t i = 0; i < nb; i++) { offs[i] = run; run += get_be32(in + fixed + 4 * i); }
+    for (size_t i = 0; i < nb; i++) {
+      const uint32_t len = get_be32(in + fixed + 4 * i);
+      if (len > MAX_STREAM) return W3_E_FORMAT;
+      offs[i] = run;
+      run += len;
+    }
     offs[nb] = run;
-    if (hdr + run != n_in) return W3_E_FORMAT;
+    if (whole && hdr + run != n_in) return W3_E_FORMAT;
   }
-  if (n > cap) return W3_E_CAP;
-  if (!nb) return W3_OK;
+  if (whole) { B0 = 0; B1 = nb; }
+  if (B0 > B1 || B1 > nb) return W3_E_ARG;
+  if (hdr + offs[B1] > n_in) return W3_E_FORMAT; /* the range's streams must be there */
+  const size_t base = B0 * bs, bytes = std::min(n, B1 * bs) - std::min(n, base);
+  *out_len = bytes;
+  if (bytes > cap) return W3_E_CAP;
+  if (B0 == B1) return W3_OK;
 
   return for_each_device(ctx, [&](int g) {
     size_t b0, b1;
-    block_range(nb, ctx->n, g, b0, b1);
+    block_range(B1 - B0, ctx->n, g, b0, b1);
     if (b0 == b1) return (int)W3_OK;
+    b0 += B0;
+    b1 += B0;
     w3_dev &d = ctx->d[g];
     CK(cudaSetDevice(d.ordinal));
     const size_t nbg = b1 - b0;
@@ -552,11 +562,25 @@ int w3_decompress(w3_ctx *ctx, const uint8_t *in, size_t n_in, uint8_t *out, siz
                         &ctx->opts, d.stream));
     uint32_t flag = 0;
     CK(cudaMemcpyAsync(&flag, d.d_flag, 4, cudaMemcpyDeviceToHost, d.stream));
-    CK(cudaMemcpyAsync(out + o0, d.out.p, obytes, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaMemcpyAsync(out + (o0 - base), d.out.p, obytes, cudaMemcpyDeviceToHost, d.stream));
     CK(cudaStreamSynchronize(d.stream));
     if (flag) return fail_msg(W3_E_CUDA, "decode kernel aborted (flag %u)", flag);
     return (int)W3_OK;
   });
+}
+
+int w3_decompress(w3_ctx *ctx, const uint8_t *in, size_t n_in, uint8_t *out, size_t cap,
+                  size_t *out_len) {
+  if (!ctx || !in || !out_len || (!out && cap)) return W3_E_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  return decode_range(ctx, in, n_in, 0, SIZE_MAX, out, cap, out_len);
+}
+
+int w3_decompress_blocks(w3_ctx *ctx, const uint8_t *in, size_t n_in, size_t first_block, size_t n_blocks,
+                         uint8_t *out, size_t cap, size_t *out_len) {
+  if (!ctx || !in || !out_len || (!out && cap) || first_block + n_blocks < first_block) return W3_E_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  return decode_range(ctx, in, n_in, first_block, first_block + n_blocks, out, cap, out_len);
 }
 
 /* ---- self-tests ------------------------------------------------------------ */

@@ -640,7 +640,13 @@ static inline uint32_t w3_per_cta(uint32_t n_blocks, int sm_count, uint32_t cap)
 }
 
 #define W3_LANE_SMEM_MAX (227u * 1024u)
-#define W3_PAIR_MAX_Q 12u /* blocks per SM up to which the pair form of the lane decoder is chosen */
+/* Measured on 1 GiB (profiles/r02_many_block_kernels.txt): the pair form of the lane decoder takes
+ * ~330 cycles per coded bit of every resident block whatever their number; the team decoder
+ * 109 cycles per bit with one block per SM, in as many waves as it takes.  Two waves of teams
+ * (218) still beat the lanes; from the third on the lanes win.  The pair form beat the lane form
+ * at every block count tried (1024 x 1 MiB: 766 against 668 MB/s; 4096 x 256 KiB: 1476 against
+ * 1312), so the lane form is only used when asked for. */
+#define W3_TEAM_MAX_WAVES 2u
 static inline uint32_t w3_lane_cap(void) { return (W3_LANE_SMEM_MAX - (uint32_t)sizeof(w3_lane_tab)) / (W3_NCTX * 4u); }
 
 extern "C" {
@@ -723,7 +729,7 @@ cudaError_t w3_launch_decode(const uint8_t *d_comp, const uint64_t *d_offsets, u
   int k = opts ? opts->kernels : W3_K_AUTO;
   /* the lane decoder counts stream bits in 32 bits: blocks it cannot be sure about go to the team kernel */
   const bool lane_ok = block_size <= (16u << 20);
-  if (k == W3_K_AUTO) k = (n_blocks > (uint32_t)sm_count && lane_ok) ? W3_K_MANY : W3_K_TEAM;
+  if (k == W3_K_AUTO) k = (n_blocks > W3_TEAM_MAX_WAVES * (uint32_t)sm_count && lane_ok) ? W3_K_MANY : W3_K_TEAM;
   if (k == W3_K_MANY && !lane_ok) k = W3_K_TEAM;
   if (k == W3_K_TEAM) {
     w3_decode_blocks_team<<<n_blocks, W3_DEC_TEAM_THREADS,
@@ -738,19 +744,16 @@ cudaError_t w3_launch_decode(const uint8_t *d_comp, const uint64_t *d_offsets, u
         d_comp, d_offsets, n_blocks, block_size, n_total, d_out, d_tab);
     return cudaGetLastError();
   }
-  /* lane per block: `resident` blocks per CTA at a time, spread over `warps` warps (one per SM
-   * sub-partition by default) of `lanes` blocks each.  Up to W3_PAIR_MAX_Q blocks per SM the chain
-   * of a block, not instruction issue, sets the pace: the pair form (two lanes per block, the next
-   * position's lookup overlapping the current bit's coder step) is used. */
+  /* lanes: `resident` blocks per CTA at a time, spread over `warps` warps (one per SM
+   * sub-partition by default) of `lanes` blocks each; the pair form (two lanes per block, the next
+   * position's lookup overlapping the current bit's coder step) unless the lane form is asked for */
   const uint32_t per = w3_per_cta(n_blocks, sm_count, w3_lane_cap());
   uint32_t warps = per < 4u ? per : 4u;
   if (opts && opts->lane_warps > 0) warps = (uint32_t)opts->lane_warps < W3_LANE_MAX_WARPS ? (uint32_t)opts->lane_warps : W3_LANE_MAX_WARPS;
   if (warps > per) warps = per;
   uint32_t lanes = w3_ceil_div(per, warps);
   while (warps * lanes > w3_lane_cap()) lanes--; /* rounding up may overshoot what fits */
-  const uint32_t q = w3_ceil_div(n_blocks, (uint32_t)sm_count);
-  bool pair = q <= W3_PAIR_MAX_Q;
-  if (opts && opts->lane_form) pair = opts->lane_form == 2;
+  const bool pair = !(opts && opts->lane_form == 1);
   if (pair && lanes > 16u) lanes = 16u;
   const uint32_t resident = warps * lanes;
   uint32_t grid = w3_ceil_div(n_blocks, resident);
