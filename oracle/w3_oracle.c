@@ -296,19 +296,43 @@ uint32_t w3o_achash(uint64_t bits, uint64_t pos, int *steps) {
 
 #define BITS_IN_CONTEXT 11 /* main.rs:151 */
 #define ALIGNMENT_BITS 3   /* main.rs:151 */
+#define HASH_MAX_BITS 8    /* main.rs:151: ACHistory::new(8, ...) */
 
 typedef struct {
-  uint16_t stats[1 << BITS_IN_CONTEXT][2]; /* ordern_entropy.rs:17 */
+  uint16_t (*stats)[2]; /* Vec<Counter>, 1 << bits_in_context entries — ordern_entropy.rs:17 */
   uint32_t ctx;
   uint8_t alignment;
+  uint8_t bits_in_context; /* ordern_entropy.rs:10 */
+  uint8_t alignment_bits;  /* :11 */
+  uint8_t max_bits;   /* ACHistory.max_bits — ac_history.rs:12, a parameter of its own (:16-18) */
   uint64_t hist_pos;  /* ACHistory.pos  ac_history.rs:10 */
   uint64_t hist_bits; /* ACHistory.bits ac_history.rs:11 */
   const uint16_t *table; /* StationaryModel.table  stationary.rs:9 */
 } model;
 
-static void model_init(model *m, const uint16_t *table) {
-  memset(m, 0, sizeof *m); /* ordern_entropy.rs:15-24, ac_history.rs:17-19 */
+/* OrderNEntropy::new(bits_in_context, alignment_bits, ACHistory::new(max_bits, model)) —
+ * ordern_entropy.rs:15-24, ac_history.rs:16-18 */
+static model *model_new(const uint16_t *table, int bits_in_context, int alignment_bits, int max_bits) {
+  model *m = (model *)calloc(1, sizeof *m);
+  if (!m) return NULL;
+  m->stats = (uint16_t(*)[2])calloc((size_t)1 << bits_in_context, sizeof(uint16_t[2]));
+  if (!m->stats) {
+    free(m);
+    return NULL;
+  }
+  m->bits_in_context = (uint8_t)bits_in_context;
+  m->alignment_bits = (uint8_t)alignment_bits;
+  m->max_bits = (uint8_t)max_bits;
   m->table = table ? table : W3O_BOOK1_TABLE; /* main.rs:151 */
+  return m;
+}
+static void model_free(model *m) {
+  if (m) free(m->stats);
+  free(m);
+}
+/* init_model — main.rs:146-152 */
+static model *model_init(const uint16_t *table) {
+  return model_new(table, BITS_IN_CONTEXT, ALIGNMENT_BITS, HASH_MAX_BITS);
 }
 
 static inline uint16_t model_predict(const model *m) {
@@ -320,14 +344,14 @@ static inline void model_update(model *m, unsigned bit) {
   /* blanket impl models/mod.rs:28-31: adapt, then update */
   w3o_counter_update(m->stats[m->ctx], (int)bit); /* ordern_entropy.rs:32-34 */
   /* ordern_entropy.rs:36-45 */
-  const uint32_t mask_bits = BITS_IN_CONTEXT - ALIGNMENT_BITS;
-  const uint32_t mask = (1u << mask_bits) - 1;
-  const uint8_t alignment_mask = (1u << ALIGNMENT_BITS) - 1;
+  const uint32_t mask_bits = (uint32_t)m->bits_in_context - m->alignment_bits;
+  const uint32_t mask = (uint32_t)(((uint64_t)1 << mask_bits) - 1);
+  const uint8_t alignment_mask = (uint8_t)((1u << m->alignment_bits) - 1);
   m->hist_bits = (m->hist_bits << 1) | bit; /* ac_history.rs:24 */
   m->hist_pos += 1;                         /* ac_history.rs:25 */
   m->alignment = (uint8_t)((m->alignment + 1) & alignment_mask);
-  uint32_t hash = w3o_achash_ex(m->hist_bits, m->hist_pos, m->table, (int)mask_bits, NULL) & mask;
-  m->ctx = (hash << ALIGNMENT_BITS) | m->alignment;
+  uint32_t hash = w3o_achash_ex(m->hist_bits, m->hist_pos, m->table, (int)m->max_bits, NULL) & mask;
+  m->ctx = (hash << m->alignment_bits) | m->alignment;
 }
 
 /* ------------------------------------------------------------------------ */
@@ -354,10 +378,21 @@ void w3o_stationary_new(const uint8_t *buf, size_t n, uint16_t table[8]) {
 
 int w3o_compress_block_ex(const uint8_t *in, size_t n, const uint16_t *table, uint8_t *out,
                           size_t cap, size_t *out_len) {
-  if ((!in && n) || (!out && cap) || !out_len) return W3O_E_ARG;
-  model *m = (model *)malloc(sizeof *m);
+  return w3o_compress_block_geo(in, n, table, BITS_IN_CONTEXT, ALIGNMENT_BITS, HASH_MAX_BITS, out, cap, out_len);
+}
+
+static int geo_ok(int bits_in_context, int alignment_bits, int max_bits) {
+  return bits_in_context >= 1 && bits_in_context <= 30 && alignment_bits >= 0 && alignment_bits <= 7 &&
+         alignment_bits <= bits_in_context && max_bits >= 1 && max_bits <= 32;
+}
+
+/* compress loop (main.rs:99-111) for any OrderNEntropy::new(bits_in_context, alignment_bits,
+ * ACHistory::new(max_bits, StationaryModel::from_table(table))) */
+int w3o_compress_block_geo(const uint8_t *in, size_t n, const uint16_t *table, int bits_in_context,
+                           int alignment_bits, int max_bits, uint8_t *out, size_t cap, size_t *out_len) {
+  if ((!in && n) || (!out && cap) || !out_len || !geo_ok(bits_in_context, alignment_bits, max_bits)) return W3O_E_ARG;
+  model *m = model_new(table, bits_in_context, alignment_bits, max_bits);
   if (!m) return W3O_E_ARG;
-  model_init(m, table);
   w3o_writer w;
   writer_init(&w, out, cap);
   coder ac;
@@ -372,7 +407,7 @@ int w3o_compress_block_ex(const uint8_t *in, size_t n, const uint16_t *table, ui
     }
   }
   writer_flush(&w, ac.x2); /* main.rs:111 → arithmetic_coder.rs:67-71 */
-  free(m);
+  model_free(m);
   *out_len = w.len;
   return w.len > cap ? W3O_E_CAP : W3O_OK;
 }
@@ -384,10 +419,14 @@ int w3o_decompress_block(const uint8_t *in, size_t n_in, uint8_t *out,
 
 int w3o_decompress_block_ex(const uint8_t *in, size_t n_in, const uint16_t *table, uint8_t *out,
                             size_t n_out) {
-  if ((!in && n_in) || (!out && n_out)) return W3O_E_ARG;
-  model *m = (model *)malloc(sizeof *m);
+  return w3o_decompress_block_geo(in, n_in, table, BITS_IN_CONTEXT, ALIGNMENT_BITS, HASH_MAX_BITS, out, n_out);
+}
+
+int w3o_decompress_block_geo(const uint8_t *in, size_t n_in, const uint16_t *table, int bits_in_context,
+                             int alignment_bits, int max_bits, uint8_t *out, size_t n_out) {
+  if ((!in && n_in) || (!out && n_out) || !geo_ok(bits_in_context, alignment_bits, max_bits)) return W3O_E_ARG;
+  model *m = model_new(table, bits_in_context, alignment_bits, max_bits);
   if (!m) return W3O_E_ARG;
-  model_init(m, table);
   w3o_reader r;
   reader_init(&r, in, n_in);
   coder ac;
@@ -403,21 +442,71 @@ int w3o_decompress_block_ex(const uint8_t *in, size_t n_in, const uint16_t *tabl
     }
     out[i] = (uint8_t)byte; /* :139 */
   }
-  free(m);
+  model_free(m);
+  return W3O_OK;
+}
+
+/* ------------------------------------------------------------------------ */
+/* ACStats — src/helpers.rs:60-90: the bit-counting ACWrite sink of the sweep */
+/* binaries; exec() — src/bin/entropy-hashing-ac/main.rs:48-75                */
+
+typedef struct {
+  uint64_t bit_count, rev_bits;
+} acstats;
+
+/* ac.encode(bit, p, &mut ACStats) — arithmetic_coder.rs:41-65 with helpers.rs:76-89 as the sink */
+static inline void ac_encode_stats(coder *c, unsigned bit, uint16_t prob, acstats *io) {
+  uint32_t xmid = lerp(c->x1, c->x2, prob);
+  if (bit == 0) c->x1 = xmid + 1;
+  else c->x2 = xmid;
+  while (((c->x1 ^ c->x2) >> PREC_SHIFT) == 0) {
+    io->bit_count += 1 + io->rev_bits; /* write_bit — helpers.rs:81-85 */
+    io->rev_bits = 0;
+    c->x1 <<= 1;
+    c->x2 = (c->x2 << 1) | 1;
+  }
+  while (c->x1 >= Q1 && c->x2 < Q3) {
+    io->rev_bits += 1; /* inc_parity — helpers.rs:77-79 */
+    c->x1 = (c->x1 << 1) & RLO_MOD;
+    c->x2 = (c->x2 << 1) | RHI_MOD;
+  }
+}
+
+/* exec(buf, ctx_bits, alignment_bits, ACHistory::new(ctx_bits - alignment_bits, model)) of the
+ * entropy-hashing-ac sweep (src/bin/entropy-hashing-ac/main.rs:24-25, 48-75): returns the number of
+ * bits ACStats counted; csize as printed is that / 8 (helpers.rs:71-73); ac.flush adds nothing
+ * (ACStats::flush is a no-op, helpers.rs:87-89). */
+int w3o_sweep_exec(const uint8_t *buf, size_t n, const uint16_t *table, int ctx_bits, int alignment_bits,
+                   uint64_t *bit_count) {
+  const int max_bits = ctx_bits - alignment_bits; /* main.rs:24 of that bin */
+  if ((!buf && n) || !bit_count || !geo_ok(ctx_bits, alignment_bits, max_bits)) return W3O_E_ARG;
+  model *m = model_new(table, ctx_bits, alignment_bits, max_bits);
+  if (!m) return W3O_E_ARG;
+  coder ac;
+  coder_init(&ac);
+  acstats w = {0, 0};
+  for (size_t i = 0; i < n; i++)
+    for (int k = 7; k >= 0; k--) { /* unroll_for!(bit in byte, …) — macros.rs:2-21 */
+      unsigned bit = (buf[i] >> k) & 1;
+      uint16_t p = model_predict(m);   /* :56 */
+      model_update(m, bit);            /* :57 */
+      ac_encode_stats(&ac, bit, p, &w); /* :58 */
+    }
+  model_free(m);
+  *bit_count = w.bit_count;
   return W3O_OK;
 }
 
 void w3o_ctx_trace(const uint8_t *in, size_t n, uint16_t *ctx_out) {
-  model *m = (model *)malloc(sizeof *m);
+  model *m = model_init(NULL);
   if (!m) return;
-  model_init(m, NULL);
   size_t t = 0;
   for (size_t i = 0; i < n; i++)
     for (int k = 7; k >= 0; k--) {
       ctx_out[t++] = (uint16_t)m->ctx;
       model_update(m, (in[i] >> k) & 1);
     }
-  free(m);
+  model_free(m);
 }
 
 /* header — src/main.rs:14-15, 95-96, 119-126 */

@@ -102,6 +102,18 @@ int w3o_compress_block_ex(const uint8_t *in, size_t n, const uint16_t *table, ui
                           size_t cap, size_t *out_len);
 int w3o_decompress_block_ex(const uint8_t *in, size_t n_in, const uint16_t *table, uint8_t *out,
                             size_t n_out);
+/* The same two loops for any OrderNEntropy::new(bits_in_context, alignment_bits,
+ * ACHistory::new(max_bits, StationaryModel::from_table(table))) — src/models/ordern_entropy.rs:15-24,
+ * src/history/ac_history.rs:16-18.  max_bits is a parameter of its own (main.rs:151 passes 8 = 11 - 3,
+ * the sweep binaries ctx_bits - alignment_bits, but nothing ties them).  bits_in_context <= 30. */
+int w3o_compress_block_geo(const uint8_t *in, size_t n, const uint16_t *table, int bits_in_context,
+                           int alignment_bits, int max_bits, uint8_t *out, size_t cap, size_t *out_len);
+int w3o_decompress_block_geo(const uint8_t *in, size_t n_in, const uint16_t *table, int bits_in_context,
+                             int alignment_bits, int max_bits, uint8_t *out, size_t n_out);
+/* exec() of the entropy-hashing-ac sweep binary (src/bin/entropy-hashing-ac/main.rs:48-75) into the
+ * ACStats sink (src/helpers.rs:60-90): *bit_count = bits counted; the printed csize is that / 8 */
+int w3o_sweep_exec(const uint8_t *buf, size_t n, const uint16_t *table, int ctx_bits, int alignment_bits,
+                   uint64_t *bit_count);
 /* StationaryModel::new(buf) — src/models/ac_hash/stationary.rs:14-34: the 8
  * bit-position probabilities of a buffer (index 0 = a byte's MSB) */
 void w3o_stationary_new(const uint8_t *buf, size_t n, uint16_t table[8]);

@@ -235,9 +235,39 @@ def stationary_new(buf: bytes):
     return tuple(counter_p(c[0], c[1]) for c in model)
 
 
-def compress_block(data: bytes, table=BOOK1) -> bytes:
-    """Stream after the 12-byte header — src/main.rs:99-111."""
-    sink, coder, model = ByteSink(), Coder(), OrderNEntropy(table=table)
+class StatsSink:
+    """ACStats — src/helpers.rs:60-90: counts bits, writes nothing; flush is a no-op."""
+
+    def __init__(self):
+        self.bit_count = 0
+        self.rev_bits = 0
+
+    def write_bit(self, b):  # helpers.rs:81-85
+        self.bit_count += 1 + self.rev_bits
+        self.rev_bits = 0
+
+    def inc_parity(self):  # helpers.rs:77-79
+        self.rev_bits += 1
+
+
+def sweep_exec(buf: bytes, ctx_bits: int, alignment_bits: int, table=BOOK1) -> int:
+    """exec() of the entropy-hashing-ac sweep (src/bin/entropy-hashing-ac/main.rs:24, 48-75):
+    bits counted by ACStats; the printed csize is that // 8 (helpers.rs:71-73)."""
+    sink, coder = StatsSink(), Coder()
+    model = OrderNEntropy(ctx_bits, alignment_bits, ctx_bits - alignment_bits, table)
+    for byte in buf:
+        for k in range(7, -1, -1):
+            bit = (byte >> k) & 1
+            p = model.predict()
+            model.update(bit)
+            coder.encode(bit, p, sink)
+    return sink.bit_count
+
+
+def compress_block(data: bytes, table=BOOK1, geo=(11, 3, 8)) -> bytes:
+    """Stream after the 12-byte header — src/main.rs:99-111; geo = (bits_in_context,
+    alignment_bits, max_bits) of OrderNEntropy::new / ACHistory::new (init_model: 11, 3, 8)."""
+    sink, coder, model = ByteSink(), Coder(), OrderNEntropy(*geo, table=table)
     for byte in data:
         for k in range(7, -1, -1):
             bit = (byte >> k) & 1
@@ -248,9 +278,9 @@ def compress_block(data: bytes, table=BOOK1) -> bytes:
     return bytes(sink.out)
 
 
-def decompress_block(stream: bytes, n_out: int, table=BOOK1) -> bytes:
+def decompress_block(stream: bytes, n_out: int, table=BOOK1, geo=(11, 3, 8)) -> bytes:
     """src/main.rs:127-140."""
-    src, coder, model = BitSource(stream), Coder(), OrderNEntropy(table=table)
+    src, coder, model = BitSource(stream), Coder(), OrderNEntropy(*geo, table=table)
     coder.start_decode(src)
     out = bytearray()
     for _ in range(n_out):

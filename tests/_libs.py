@@ -74,6 +74,9 @@ def load_oracle():
     o.w3o_compress_block_ex.argtypes = [u8p, sz, u16p, C.c_void_p, sz, C.POINTER(sz)]
     o.w3o_decompress_block_ex.argtypes = [u8p, sz, u16p, C.c_void_p, sz]
     o.w3o_stationary_new.argtypes = [u8p, sz, u16p]
+    o.w3o_compress_block_geo.argtypes = [u8p, sz, u16p, C.c_int, C.c_int, C.c_int, C.c_void_p, sz, C.POINTER(sz)]
+    o.w3o_decompress_block_geo.argtypes = [u8p, sz, u16p, C.c_int, C.c_int, C.c_int, C.c_void_p, sz]
+    o.w3o_sweep_exec.argtypes = [u8p, sz, u16p, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
     o.w3o_compress_file.argtypes = [u8p, sz, C.c_void_p, sz, C.POINTER(sz)]
     o.w3o_decompress_file.argtypes = [u8p, sz, C.c_void_p, sz, C.POINTER(sz)]
     o.w3o_ctx_trace.argtypes = [u8p, sz, u16p]
@@ -122,6 +125,31 @@ class Oracle:
         rc = self.lib.w3o_decompress_block_ex(stream, len(stream), t, out, n_out)
         assert rc == 0, rc
         return out.raw[:n_out]
+
+    def compress_block_geo(self, data: bytes, ctx_bits: int, align_bits: int, max_bits: int, table=None) -> bytes:
+        n = len(data)
+        cap = 17 * n + 64
+        out = C.create_string_buffer(cap)
+        ol = C.c_size_t()
+        t = (C.c_uint16 * 8)(*table) if table is not None else None
+        rc = self.lib.w3o_compress_block_geo(data, n, t, ctx_bits, align_bits, max_bits, out, cap, C.byref(ol))
+        assert rc == 0, rc
+        return out.raw[: ol.value]
+
+    def decompress_block_geo(self, stream: bytes, n_out: int, ctx_bits: int, align_bits: int, max_bits: int, table=None) -> bytes:
+        out = C.create_string_buffer(max(n_out, 1))
+        t = (C.c_uint16 * 8)(*table) if table is not None else None
+        rc = self.lib.w3o_decompress_block_geo(stream, len(stream), t, ctx_bits, align_bits, max_bits, out, n_out)
+        assert rc == 0, rc
+        return out.raw[:n_out]
+
+    def sweep_exec(self, data: bytes, ctx_bits: int, align_bits: int, table=None) -> int:
+        """bits ACStats counts for one point of the entropy-hashing-ac sweep (csize = // 8)"""
+        t = (C.c_uint16 * 8)(*table) if table is not None else None
+        bc = C.c_uint64()
+        rc = self.lib.w3o_sweep_exec(data, len(data), t, ctx_bits, align_bits, C.byref(bc))
+        assert rc == 0, rc
+        return bc.value
 
     def stationary_new(self, data: bytes):
         t = (C.c_uint16 * 8)()

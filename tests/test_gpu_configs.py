@@ -109,7 +109,8 @@ def test_config3_1gib_sampled_blocks_and_checksum_across_device_counts(libs):
         back = C.create_string_buffer(n)
         assert many.decompress_into(C.addressof(comp), clen, C.addressof(back), n) == n
         assert _same(back, buf, n)
-        print(f"config3 container sha256 {sha} ({clen} bytes, {len(devs)} device(s))")
+        # the constant bench.py asserts at every N (recorded from the first run on one B200)
+        assert (sha, clen) == ("8491ae22b3f6d6d0d4f66b9a86f127c6f93bb96044058007389020a7fd3eff35", 479042365)
     finally:
         one.close()
         many.close()
