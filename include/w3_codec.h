@@ -81,6 +81,35 @@ int w3_ctx_get_model(const w3_ctx *ctx, uint16_t table[8]);
  * Counter::update included (src/models/counter.rs:20-26). */
 int w3_train_model(w3_ctx *ctx, const uint8_t *in, size_t n, uint16_t table[8]);
 
+/* ---- the geometry of the model stack -----------------------------------------
+ * OrderNEntropy::new(bits_in_context, alignment_bits, ACHistory::new(max_bits, model)) —
+ * src/models/ordern_entropy.rs:15-24, src/history/ac_history.rs:16-18.  init_model() fixes
+ * (11, 3, 8) (src/main.rs:151) and that is what a fresh context uses; the reference's sweep
+ * (src/bin/entropy-hashing-ac/main.rs:20-37) walks bits_in_context 8..30 x alignment_bits 0..4
+ * with max_bits = bits_in_context - alignment_bits and finds 20 / 3 best on book1 (book1.log:76).
+ * With any other geometry than (11, 3, 8) the counter table (4 << bits_in_context bytes per
+ * block) lives in HBM, w3_compress writes container version 3 — byte 5..7 of the header =
+ * bits_in_context, alignment_bits, max_bits, then the 8 model probabilities as in version 2 —
+ * and W3_F_LEGACY fails (the reference's file format cannot say so).  w3_decompress reads the
+ * geometry from the container.  bits_in_context <= 30, alignment_bits <= 7, max_bits <= 32. */
+int w3_ctx_set_geometry(w3_ctx *ctx, int bits_in_context, int alignment_bits, int max_bits);
+int w3_ctx_get_geometry(const w3_ctx *ctx, int *bits_in_context, int *alignment_bits, int *max_bits);
+
+/* The parameter sweep of the reference's research binaries, on the GPU: every point is exec()
+ * of src/bin/entropy-hashing-ac/main.rs:48-75 — the whole of in[0..n) coded as one stream by
+ * OrderNEntropy::new(ctx_bits, alignment_bits, ACHistory::new(ctx_bits - alignment_bits, model))
+ * into the bit-counting sink ACStats (src/helpers.rs:60-90).  bit_counts[i] = bits counted for
+ * points[i]; the csize the reference prints is bit_counts[i] / 8 (helpers.rs:71-73).
+ * table = the StationaryModel probabilities, or NULL for StationaryModel::new(in) as the sweep
+ * binary does (main.rs:19 of that binary); table_used (optional) receives the 8 probabilities.
+ * All points run concurrently, each with its own counter table in HBM (4 << ctx_bits bytes),
+ * in as many batches as the first device's memory requires.  n <= 256 MiB. */
+typedef struct w3_sweep_point {
+  uint8_t ctx_bits, alignment_bits;
+} w3_sweep_point;
+int w3_sweep(w3_ctx *ctx, const uint8_t *in, size_t n, const uint16_t table[8], const w3_sweep_point *points,
+             size_t n_points, uint64_t *bit_counts, uint16_t table_used[8]);
+
 /* Upper bound of w3_compress output for n input bytes. */
 size_t w3_compress_bound(size_t n, size_t block_size);
 
@@ -89,7 +118,7 @@ size_t w3_compress_bound(size_t n, size_t block_size);
  * multiple of 4, <= 256 MiB), codes every block exactly as the reference
  * codes a file of those bytes, and writes the container
  *   "w3Bk" | u8 version | u8[3] 0 | u64 BE n | u32 BE block_size | u32 BE n_blocks
- *   | version 2 only: 8 x u16 BE StationaryModel probabilities
+ *   | versions 2 and 3: 8 x u16 BE StationaryModel probabilities (version 3: u8[3] = the geometry)
  *   | n_blocks x u32 BE stream length | streams back to back
  * or, with W3_F_LEGACY, the reference's own single-stream file. */
 int w3_compress(w3_ctx *ctx, const uint8_t *in, size_t n, size_t block_size, uint32_t flags,

@@ -20,7 +20,7 @@ DEFAULT_BLOCK = 1 << 20
 # every symbol include/w3_codec.h declares
 SYMBOLS = (
     "w3_ctx_create", "w3_ctx_destroy", "w3_ctx_device_count", "w3_ctx_set_option", "w3_compress_bound",
-    "w3_ctx_set_model", "w3_ctx_get_model", "w3_train_model",
+    "w3_ctx_set_model", "w3_ctx_get_model", "w3_train_model", "w3_ctx_set_geometry", "w3_ctx_get_geometry", "w3_sweep",
     "w3_compress", "w3_decompress", "w3_decompress_blocks", "w3_decompressed_size",
     "w3_encode_device", "w3_pack_device", "w3_decode_device",
     "w3_selftest_achash", "w3_selftest_counter_p", "w3_probe_sector_gather", "w3_selftest_ac_encode", "w3_selftest_ac_decode",
@@ -61,6 +61,9 @@ def load():
     lib.w3_ctx_set_model.argtypes = [vp, vp]
     lib.w3_ctx_get_model.argtypes = [vp, vp]
     lib.w3_train_model.argtypes = [vp, u8p, sz, vp]
+    lib.w3_ctx_set_geometry.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    lib.w3_ctx_get_geometry.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.w3_sweep.argtypes = [vp, u8p, sz, vp, vp, sz, vp, vp]
     lib.w3_compress_bound.argtypes = [sz, sz]
     lib.w3_compress_bound.restype = sz
     lib.w3_compress.argtypes = [vp, u8p, sz, sz, C.c_uint32, u8p, sz, C.POINTER(sz)]
@@ -148,6 +151,27 @@ class Context:
         arr = (C.c_uint16 * 8)()
         check(self.lib.w3_train_model(self.handle, _addr(data), len(data), C.addressof(arr)))
         return tuple(arr)
+
+    # ---- the geometry of the model stack (ordern_entropy.rs:15-24) and the sweep -----------
+    def set_geometry(self, bits_in_context: int, alignment_bits: int, max_bits: int) -> None:
+        check(self.lib.w3_ctx_set_geometry(self.handle, bits_in_context, alignment_bits, max_bits))
+
+    def get_geometry(self):
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        check(self.lib.w3_ctx_get_geometry(self.handle, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def sweep(self, data, points, table=None):
+        """exec() of src/bin/entropy-hashing-ac/main.rs:48-75 for every (ctx_bits, alignment_bits) of
+        `points`, all at once on the GPU: -> (bit counts, the StationaryModel table used)."""
+        n = len(points)
+        pts = (C.c_uint8 * (2 * n))(*[v for p in points for v in p])
+        t = (C.c_uint16 * 8)(*table) if table is not None else None
+        used = (C.c_uint16 * 8)()
+        out = (C.c_uint64 * n)()
+        check(self.lib.w3_sweep(self.handle, _addr(data), len(data), C.addressof(t) if t is not None else None,
+                                C.addressof(pts), n, C.addressof(out), C.addressof(used)))
+        return list(out), tuple(used)
 
     # ---- host-buffer API -------------------------------------------------
     def compress_bound(self, n: int, block_size: int = DEFAULT_BLOCK) -> int:

@@ -21,6 +21,7 @@
 
 #include "../../include/w3_codec.h"
 #include "w3_core.cuh"
+#include "w3_geo.h"
 #include "w3_kernels.h"
 #include "w3_tierb.cuh"
 
@@ -70,6 +71,22 @@ struct w3_buf {
     cap = want;
     return W3_OK;
   }
+  /* like ensure, but the first `keep` bytes survive a reallocation */
+  int grow_keep(size_t n, size_t keep) {
+    if (n <= cap) return W3_OK;
+    void *q = nullptr;
+    const size_t want = n + (n >> 2) + 256;
+    cudaError_t e = cudaMalloc(&q, want);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    if (p && keep) {
+      e = cudaMemcpy(q, p, keep, cudaMemcpyDeviceToDevice);
+      if (e != cudaSuccess) { cudaFree(q); return cuda_fail(e, "cudaMemcpy"); }
+    }
+    if (p) cudaFree(p);
+    p = q;
+    cap = want;
+    return W3_OK;
+  }
   void release() {
     if (p) cudaFree(p);
     p = nullptr;
@@ -82,6 +99,7 @@ struct w3_dev {
   cudaStream_t stream = nullptr;
   w3_hashtab *d_tab = nullptr;
   w3_buf in, scratch, scratch2, lens, lens2, alt, offsets, packed, out;
+  w3_buf geo_H, geo_counters, geo_jobs; /* run-time geometry (w3_geo.cu) */
   uint32_t *d_flag = nullptr;
 };
 
@@ -92,6 +110,9 @@ struct w3_ctx {
   w3_dev d[W3_MAX_DEVICES];
   uint16_t table[8]; /* the StationaryModel in force (init_model: for_book1, src/main.rs:151) */
   w3_launch_opts opts = {0, 0, 0, 0}; /* w3_ctx_set_option */
+  /* OrderNEntropy::new(bits_in_context, alignment_bits, ACHistory::new(max_bits, ..)); init_model: 11, 3, 8 */
+  int ctx_bits = W3_CTX_BITS, align_bits = W3_ALIGN_BITS, max_bits = W3_HASH_BITS;
+  bool default_geometry() const { return ctx_bits == W3_CTX_BITS && align_bits == W3_ALIGN_BITS && max_bits == W3_HASH_BITS; }
   std::mutex mu;     /* one host call at a time per context */
 };
 
@@ -151,7 +172,7 @@ static int ctx_set_model(w3_ctx *ctx, const uint16_t *table) {
 static void dev_release(w3_dev &d) {
   cudaSetDevice(d.ordinal);
   d.in.release(); d.scratch.release(); d.scratch2.release(); d.lens.release(); d.lens2.release();
-  d.alt.release(); d.offsets.release();
+  d.alt.release(); d.offsets.release(); d.geo_H.release(); d.geo_counters.release(); d.geo_jobs.release();
   d.packed.release(); d.out.release();
   if (d.d_tab) cudaFree(d.d_tab);
   if (d.d_flag) cudaFree(d.d_flag);
@@ -402,6 +423,131 @@ static int encode_part(w3_ctx *ctx, int g, const uint8_t *in, size_t n, size_t b
   return W3_OK;
 }
 
+
+/* ---- run-time geometry (w3_geo.cu) ------------------------------------------ */
+
+static bool geo_ok(int ctx_bits, int align_bits, int max_bits) {
+  return ctx_bits >= 1 && ctx_bits <= 30 && align_bits >= 0 && align_bits <= 7 && align_bits <= ctx_bits &&
+         max_bits >= 1 && max_bits <= 32;
+}
+/* blocks of one batch: the hash array costs 32 bytes per input byte, the counters 4 << ctx_bits per block */
+static size_t geo_batch_blocks(size_t bs, int ctx_bits, bool with_hash) {
+  size_t by_cnt = std::max<size_t>(1, ((size_t)16 << 30) / ((size_t)4 << ctx_bits));
+  size_t by_h = with_hash ? std::max<size_t>(1, ((size_t)8 << 30) / (32 * bs)) : by_cnt;
+  return std::min<size_t>(std::min(by_cnt, by_h), 4096);
+}
+
+/* encode blocks [b0, b1) of `in` on device g with the context's geometry; same contract as encode_part */
+static int encode_part_geo(w3_ctx *ctx, int g, const uint8_t *in, size_t n, size_t bs, enc_part &part) {
+  w3_dev &d = ctx->d[g];
+  const size_t nb = part.b1 - part.b0;
+  part.lens.assign(nb, 0);
+  part.total = 0;
+  if (!nb) return W3_OK;
+  CK(cudaSetDevice(d.ordinal));
+  const size_t off = part.b0 * bs, bytes = std::min(n, part.b1 * bs) - off;
+  int rc;
+  if ((rc = d.in.ensure(round_up(bytes, 4) + 16)) != W3_OK) return rc;
+  CK(cudaMemcpyAsync(d.in.p, in + off, bytes, cudaMemcpyHostToDevice, d.stream));
+  const size_t per = geo_batch_blocks(bs, ctx->ctx_bits, true);
+  const size_t nbat = std::min(per, nb);
+  size_t stride = round_up(bs + (bs >> 3) + 64, 16);
+  if ((rc = d.geo_H.ensure(nbat * bs * 32 + 64)) != W3_OK) return rc;
+  if ((rc = d.geo_counters.ensure(nbat * ((size_t)4 << ctx->ctx_bits))) != W3_OK) return rc;
+  if ((rc = d.geo_jobs.ensure(nbat * sizeof(w3_geo_job))) != W3_OK) return rc;
+  if ((rc = d.scratch.ensure(stride * nbat)) != W3_OK) return rc;
+  if ((rc = d.lens.ensure(nbat * 4)) != W3_OK) return rc;
+  if ((rc = d.offsets.ensure((nbat + 1) * 8)) != W3_OK) return rc;
+  if ((rc = d.packed.ensure(bytes + (bytes >> 3) + 64 * (nb + 1))) != W3_OK) return rc;
+  const uint16_t *d_table = &d.d_tab->table[0];
+  std::vector<w3_geo_job> jobs(nbat);
+  uint64_t packed_at = 0;
+  for (size_t first = 0; first < nb; first += nbat) {
+    const size_t cnt = std::min(nbat, nb - first);
+    const size_t boff = first * bs, blen = std::min(bytes, (first + cnt) * bs) - boff;
+    for (int attempt = 0;; attempt++) {
+      CK(w3_launch_geo_hash((const uint8_t *)d.in.p + boff, blen, (uint32_t)bs, d_table, (uint32_t)ctx->max_bits,
+                            (uint32_t *)d.geo_H.p, d.sm_count, d.stream));
+      CK(cudaMemsetAsync(d.geo_counters.p, 0, cnt * ((size_t)4 << ctx->ctx_bits), d.stream));
+      for (size_t i = 0; i < cnt; i++) {
+        w3_geo_job &j = jobs[i];
+        memset(&j, 0, sizeof j);
+        j.H = (const uint32_t *)d.geo_H.p + i * bs * 8;
+        j.in = (const uint8_t *)d.in.p + boff + i * bs;
+        j.out = (uint8_t *)d.scratch.p + i * stride;
+        j.counters = (uint32_t *)d.geo_counters.p + i * ((size_t)1 << ctx->ctx_bits);
+        j.nbytes = (uint32_t)std::min(bs, blen - i * bs);
+        j.cap = (uint32_t)std::min<size_t>(stride, 0xFFFFFFF0u);
+        j.ctx_bits = (uint32_t)ctx->ctx_bits;
+        j.align_bits = (uint32_t)ctx->align_bits;
+      }
+      CK(cudaMemcpyAsync(d.geo_jobs.p, jobs.data(), cnt * sizeof(w3_geo_job), cudaMemcpyHostToDevice, d.stream));
+      CK(w3_launch_geo_encode((w3_geo_job *)d.geo_jobs.p, (uint32_t)cnt, 1u, d.stream));
+      CK(cudaMemcpyAsync(jobs.data(), d.geo_jobs.p, cnt * sizeof(w3_geo_job), cudaMemcpyDeviceToHost, d.stream));
+      CK(cudaStreamSynchronize(d.stream));
+      uint64_t need = 0;
+      for (size_t i = 0; i < cnt; i++) if (jobs[i].flags) need = std::max<uint64_t>(need, jobs[i].out_len);
+      if (!need) break;
+      if (attempt || need > MAX_STREAM) return fail_msg(W3_E_TOOBIG, "a block's stream is %llu bytes", (unsigned long long)need);
+      stride = round_up((size_t)need + 64, 16); /* every stream reports its full length: the second pass fits */
+      if ((rc = d.scratch.ensure(stride * nbat)) != W3_OK) return rc;
+    }
+    std::vector<uint32_t> lens(cnt);
+    for (size_t i = 0; i < cnt; i++) { lens[i] = jobs[i].out_len; part.lens[first + i] = lens[i]; }
+    CK(cudaMemcpyAsync(d.lens.p, lens.data(), cnt * 4, cudaMemcpyHostToDevice, d.stream));
+    uint64_t batch_total = 0;
+    for (uint32_t l : lens) batch_total += l;
+    if ((rc = d.packed.grow_keep(packed_at + batch_total + 16, packed_at)) != W3_OK) return rc; /* grows only after an overflow */
+    CK(w3_launch_pack((const uint8_t *)d.scratch.p, stride, (const uint32_t *)d.lens.p, (uint32_t)cnt,
+                      (uint64_t *)d.offsets.p, nullptr, (uint8_t *)d.packed.p + packed_at, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    packed_at += batch_total;
+  }
+  part.total = packed_at;
+  return W3_OK;
+}
+
+/* decode blocks [b0, b1) (streams at in + hdr + offs[]) on device g with the given geometry */
+static int decode_part_geo(w3_ctx *ctx, int g, const uint8_t *streams, const std::vector<uint64_t> &offs, size_t b0,
+                           size_t b1, size_t bs, size_t n, int ctx_bits, int align_bits, int max_bits, uint8_t *out_base,
+                           size_t base) {
+  w3_dev &d = ctx->d[g];
+  CK(cudaSetDevice(d.ordinal));
+  const size_t nbg = b1 - b0;
+  const uint64_t c0 = offs[b0], clen = offs[b1] - c0;
+  const size_t o0 = b0 * bs, obytes = std::min(n, b1 * bs) - o0;
+  int rc;
+  if ((rc = d.packed.ensure(clen + 16)) != W3_OK) return rc;
+  if ((rc = d.out.ensure(round_up(obytes, 4) + 16)) != W3_OK) return rc;
+  const size_t nbat = std::min(geo_batch_blocks(bs, ctx_bits, false), nbg);
+  if ((rc = d.geo_counters.ensure(nbat * ((size_t)4 << ctx_bits))) != W3_OK) return rc;
+  if ((rc = d.geo_jobs.ensure(nbat * sizeof(w3_geo_job))) != W3_OK) return rc;
+  if (clen) CK(cudaMemcpyAsync(d.packed.p, streams + c0, clen, cudaMemcpyHostToDevice, d.stream));
+  std::vector<w3_geo_job> jobs(nbat);
+  for (size_t first = 0; first < nbg; first += nbat) {
+    const size_t cnt = std::min(nbat, nbg - first);
+    CK(cudaMemsetAsync(d.geo_counters.p, 0, cnt * ((size_t)4 << ctx_bits), d.stream));
+    for (size_t i = 0; i < cnt; i++) {
+      w3_geo_job &j = jobs[i];
+      memset(&j, 0, sizeof j);
+      const size_t b = b0 + first + i;
+      j.in = (const uint8_t *)d.packed.p + (offs[b] - c0);
+      j.out_len = (uint32_t)(offs[b + 1] - offs[b]);
+      j.out = (uint8_t *)d.out.p + (first + i) * bs;
+      j.counters = (uint32_t *)d.geo_counters.p + i * ((size_t)1 << ctx_bits);
+      j.nbytes = (uint32_t)(std::min(n, (b + 1) * bs) - b * bs);
+      j.ctx_bits = (uint32_t)ctx_bits;
+      j.align_bits = (uint32_t)align_bits;
+    }
+    CK(cudaMemcpyAsync(d.geo_jobs.p, jobs.data(), cnt * sizeof(w3_geo_job), cudaMemcpyHostToDevice, d.stream));
+    CK(w3_launch_geo_decode((w3_geo_job *)d.geo_jobs.p, (uint32_t)cnt, 1u, &d.d_tab->table[0], (uint32_t)max_bits, d.stream));
+    CK(cudaStreamSynchronize(d.stream)); /* jobs[] is reused by the next batch */
+  }
+  CK(cudaMemcpyAsync(out_base + (o0 - base), d.out.p, obytes, cudaMemcpyDeviceToHost, d.stream));
+  CK(cudaStreamSynchronize(d.stream));
+  return W3_OK;
+}
+
 int w3_compress(w3_ctx *ctx, const uint8_t *in, size_t n, size_t block_size, uint32_t flags,
                 uint8_t *out, size_t cap, size_t *out_len) {
   if (!ctx || !out_len || (!in && n) || (!out && cap)) return W3_E_ARG;
@@ -420,7 +566,8 @@ int w3_compress(w3_ctx *ctx, const uint8_t *in, size_t n, size_t block_size, uin
   const size_t nb = legacy ? 1 : (n + block_size - 1) / block_size;
   if (nb > 0xFFFFFFFFull) return W3_E_ARG;
   /* the reference's file format has no room for a model: it implies for_book1 */
-  const bool custom = memcmp(ctx->table, BOOK1, sizeof BOOK1) != 0;
+  const bool geo = !ctx->default_geometry(); /* container version 3: geometry and model in the header */
+  const bool custom = geo || memcmp(ctx->table, BOOK1, sizeof BOOK1) != 0;
   if (legacy && custom) return W3_E_ARG;
   const size_t fixed = HDR_BLOCKS + (custom ? HDR_MODEL : 0);
   const size_t hdr = legacy ? HDR_LEGACY : fixed + 4 * nb;
@@ -433,7 +580,9 @@ int w3_compress(w3_ctx *ctx, const uint8_t *in, size_t n, size_t block_size, uin
     parts[0].b0 = 0; parts[0].b1 = 1;
     for (int g = 1; g < ctx->n; g++) parts[g].b0 = parts[g].b1 = 1;
   }
-  rc = for_each_device(ctx, [&](int g) { return encode_part(ctx, g, in, n, block_size, parts[g]); });
+  rc = for_each_device(ctx, [&](int g) {
+    return geo ? encode_part_geo(ctx, g, in, n, block_size, parts[g]) : encode_part(ctx, g, in, n, block_size, parts[g]);
+  });
   if (rc != W3_OK) return rc;
 
   uint64_t total = 0;
@@ -446,7 +595,8 @@ int w3_compress(w3_ctx *ctx, const uint8_t *in, size_t n, size_t block_size, uin
     put_be64(out + 4, (uint64_t)n); /* main.rs:96 */
   } else {
     memcpy(out, MAGIC_BLOCKS, 4);
-    out[4] = custom ? 2 : 1; out[5] = out[6] = out[7] = 0;
+    out[4] = geo ? 3 : custom ? 2 : 1;
+    out[5] = geo ? (uint8_t)ctx->ctx_bits : 0; out[6] = geo ? (uint8_t)ctx->align_bits : 0; out[7] = geo ? (uint8_t)ctx->max_bits : 0;
     put_be64(out + 8, (uint64_t)n);
     put_be32(out + 16, (uint32_t)block_size);
     put_be32(out + 20, (uint32_t)nb);
@@ -477,8 +627,9 @@ int w3_decompressed_size(const uint8_t *in, size_t n_in, size_t *out_len) {
     return W3_OK;
   }
   if (!memcmp(in, MAGIC_BLOCKS, 4)) {
-    if (n_in < HDR_BLOCKS || (in[4] != 1 && in[4] != 2)) return W3_E_FORMAT;
-    if (in[4] == 2 && n_in < HDR_BLOCKS + HDR_MODEL) return W3_E_FORMAT;
+    if (n_in < HDR_BLOCKS || in[4] < 1 || in[4] > 3) return W3_E_FORMAT;
+    if (in[4] >= 2 && n_in < HDR_BLOCKS + HDR_MODEL) return W3_E_FORMAT;
+    if (in[4] == 3 && !geo_ok(in[5], in[6], in[7])) return W3_E_FORMAT;
     *out_len = (size_t)get_be64(in + 8);
     return W3_OK;
   }
@@ -494,6 +645,7 @@ static int decode_range(w3_ctx *ctx, const uint8_t *in, size_t n_in, size_t B0, 
   const bool whole = B1 == SIZE_MAX;
 
   size_t bs, nb, hdr;
+  int g_ctx = W3_CTX_BITS, g_align = W3_ALIGN_BITS, g_max = W3_HASH_BITS; /* version 3: from the header */
   std::vector<uint64_t> offs; /* nb + 1, relative to the first stream byte */
   if (!memcmp(in, MAGIC_LEGACY, 4)) {
     /* one stream running to the end of the file; a short file decodes with
@@ -509,13 +661,14 @@ static int decode_range(w3_ctx *ctx, const uint8_t *in, size_t n_in, size_t B0, 
     bs = get_be32(in + 16);
     nb = get_be32(in + 20);
     if (!bs || (bs & 3) || bs > MAX_BLOCK || nb != (n + bs - 1) / bs) return W3_E_FORMAT;
-    const size_t fixed = HDR_BLOCKS + (in[4] == 2 ? HDR_MODEL : 0);
+    const size_t fixed = HDR_BLOCKS + (in[4] >= 2 ? HDR_MODEL : 0);
     hdr = fixed + 4 * nb;
     if (n_in < hdr) return W3_E_FORMAT;
-    /* a version-2 container carries its StationaryModel; version 1 means for_book1 */
+    if (in[4] == 3) { g_ctx = in[5]; g_align = in[6]; g_max = in[7]; }
+    /* version-2 and -3 containers carry their StationaryModel; version 1 means for_book1 */
     uint16_t table[8];
     for (int i = 0; i < 8; i++)
-      table[i] = in[4] == 2 ? (uint16_t)((in[HDR_BLOCKS + 2 * i] << 8) | in[HDR_BLOCKS + 2 * i + 1]) : BOOK1[i];
+      table[i] = in[4] >= 2 ? (uint16_t)((in[HDR_BLOCKS + 2 * i] << 8) | in[HDR_BLOCKS + 2 * i + 1]) : BOOK1[i];
     if ((rc = ctx_set_model(ctx, table)) != W3_OK) return rc;
     offs.resize(nb + 1);
     uint64_t run = 0;
@@ -542,6 +695,8 @@ static int decode_range(w3_ctx *ctx, const uint8_t *in, size_t n_in, size_t B0, 
     if (b0 == b1) return (int)W3_OK;
     b0 += B0;
     b1 += B0;
+    if (g_ctx != W3_CTX_BITS || g_align != W3_ALIGN_BITS || g_max != W3_HASH_BITS)
+      return decode_part_geo(ctx, g, in + hdr, offs, b0, b1, bs, n, g_ctx, g_align, g_max, out, base);
     w3_dev &d = ctx->d[g];
     CK(cudaSetDevice(d.ordinal));
     const size_t nbg = b1 - b0;
@@ -581,6 +736,95 @@ int w3_decompress_blocks(w3_ctx *ctx, const uint8_t *in, size_t n_in, size_t fir
   if (!ctx || !in || !out_len || (!out && cap) || first_block + n_blocks < first_block) return W3_E_ARG;
   std::lock_guard<std::mutex> lock(ctx->mu);
   return decode_range(ctx, in, n_in, first_block, first_block + n_blocks, out, cap, out_len);
+}
+
+int w3_ctx_set_geometry(w3_ctx *ctx, int bits_in_context, int alignment_bits, int max_bits) {
+  if (!ctx || !geo_ok(bits_in_context, alignment_bits, max_bits)) return W3_E_ARG;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  ctx->ctx_bits = bits_in_context;
+  ctx->align_bits = alignment_bits;
+  ctx->max_bits = max_bits;
+  return W3_OK;
+}
+int w3_ctx_get_geometry(const w3_ctx *ctx, int *bits_in_context, int *alignment_bits, int *max_bits) {
+  if (!ctx || !bits_in_context || !alignment_bits || !max_bits) return W3_E_ARG;
+  std::lock_guard<std::mutex> lock(const_cast<w3_ctx *>(ctx)->mu);
+  *bits_in_context = ctx->ctx_bits;
+  *alignment_bits = ctx->align_bits;
+  *max_bits = ctx->max_bits;
+  return W3_OK;
+}
+
+/* the sweep of src/bin/entropy-hashing-ac/main.rs:20-37: every point is exec() (:48-75) into ACStats */
+int w3_sweep(w3_ctx *ctx, const uint8_t *in, size_t n, const uint16_t *table, const w3_sweep_point *points,
+             size_t n_points, uint64_t *bit_counts, uint16_t *table_used) {
+  if (!ctx || (!in && n) || !points || !bit_counts || !n_points || n_points > 4096 || n > ((size_t)1 << 28)) return W3_E_ARG;
+  int hmax = 0;
+  for (size_t i = 0; i < n_points; i++) {
+    const int mb = (int)points[i].ctx_bits - (int)points[i].alignment_bits; /* ACHistory::new(ctx_bits - alignment_bits, ..) — :24 */
+    if (!geo_ok(points[i].ctx_bits, points[i].alignment_bits, mb)) return W3_E_ARG;
+    hmax = std::max(hmax, mb);
+  }
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  w3_dev &d = ctx->d[0];
+  CK(cudaSetDevice(d.ordinal));
+  int rc;
+  const size_t n_chunks = (n + 1023) / 1024;
+  if ((rc = d.in.ensure(round_up(n, 4) + 16)) != W3_OK) return rc;
+  if ((rc = d.scratch.ensure(n_chunks * 16 + 16)) != W3_OK) return rc;
+  if ((rc = d.offsets.ensure(64)) != W3_OK) return rc;
+  if ((rc = d.geo_H.ensure(n * 32 + 64)) != W3_OK) return rc;
+  if ((rc = d.geo_jobs.ensure(n_points * sizeof(w3_geo_job))) != W3_OK) return rc;
+  CK(cudaMemsetAsync(d.in.p, 0, round_up(n, 4) + 16, d.stream));
+  if (n) CK(cudaMemcpyAsync(d.in.p, in, n, cudaMemcpyHostToDevice, d.stream));
+  uint16_t *d_table = (uint16_t *)d.offsets.p;
+  if (table) CK(cudaMemcpyAsync(d_table, table, 16, cudaMemcpyHostToDevice, d.stream));
+  else CK(w3_launch_train((const uint8_t *)d.in.p, n, (uint16_t *)d.scratch.p, d_table, d.sm_count, d.stream)); /* StationaryModel::new(&buf) — :19 */
+  if (table_used) CK(cudaMemcpyAsync(table_used, d_table, 16, cudaMemcpyDeviceToHost, d.stream));
+  /* one hash pass at the largest max_bits: a shorter hash is a prefix of a longer one */
+  CK(w3_launch_geo_hash((const uint8_t *)d.in.p, n, (uint32_t)std::max<size_t>(round_up(n, 4), 4), d_table, (uint32_t)hmax,
+                        (uint32_t *)d.geo_H.p, d.sm_count, d.stream));
+  /* points in batches whose counter tables fit the device's free memory */
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  const size_t budget = std::max<size_t>((size_t)4 << 30, (free_b + d.geo_counters.cap) / 10 * 8);
+  std::vector<size_t> order(n_points);
+  for (size_t i = 0; i < n_points; i++) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return points[a].ctx_bits > points[b].ctx_bits; });
+  std::vector<w3_geo_job> jobs;
+  for (size_t at = 0; at < n_points;) {
+    size_t used = 0, cnt = 0;
+    while (at + cnt < n_points) {
+      const size_t sz = (size_t)4 << points[order[at + cnt]].ctx_bits;
+      if (cnt && used + sz > budget) break;
+      used += sz;
+      cnt++;
+    }
+    if ((rc = d.geo_counters.ensure(used)) != W3_OK) return rc;
+    CK(cudaMemsetAsync(d.geo_counters.p, 0, used, d.stream));
+    jobs.assign(cnt, w3_geo_job());
+    size_t coff = 0;
+    for (size_t i = 0; i < cnt; i++) {
+      const w3_sweep_point &pt = points[order[at + i]];
+      w3_geo_job &j = jobs[i];
+      memset(&j, 0, sizeof j);
+      j.H = (const uint32_t *)d.geo_H.p;
+      j.in = (const uint8_t *)d.in.p;
+      j.out = nullptr; /* ACStats: count only */
+      j.counters = (uint32_t *)((uint8_t *)d.geo_counters.p + coff);
+      coff += (size_t)4 << pt.ctx_bits;
+      j.nbytes = (uint32_t)n;
+      j.ctx_bits = pt.ctx_bits;
+      j.align_bits = pt.alignment_bits;
+    }
+    CK(cudaMemcpyAsync(d.geo_jobs.p, jobs.data(), cnt * sizeof(w3_geo_job), cudaMemcpyHostToDevice, d.stream));
+    CK(w3_launch_geo_encode((w3_geo_job *)d.geo_jobs.p, (uint32_t)cnt, 1u, d.stream));
+    CK(cudaMemcpyAsync(jobs.data(), d.geo_jobs.p, cnt * sizeof(w3_geo_job), cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    for (size_t i = 0; i < cnt; i++) bit_counts[order[at + i]] = jobs[i].bit_count;
+    at += cnt;
+  }
+  return W3_OK;
 }
 
 /* ---- self-tests ------------------------------------------------------------ */
