@@ -258,23 +258,24 @@ int hs_pair_decode_block(const w3_hashtab *tab, const uint8_t *in, size_t n_in, 
   std::vector<uint32_t> cnt0(W3_NCTX, 0u), cnt1(W3_NCTX, 0u);
   const w3_lane_mem m[2] = {env.mem(cnt0.data(), tab), env.mem(cnt1.data(), tab)};
   w3_pair_dec s[2];
-  for (uint32_t g = 0; g < 2; g++) {
-    w3_pair_init(s[g], ab, bp0, end_bits);
-    w3_pair_back(s[g], g, 1u, m[g]);
-  }
+  for (uint32_t g = 0; g < 2; g++) w3_pair_init(s[g], ab, bp0, end_bits);
   for (size_t i = 0; i < n_out; i++) {
     uint32_t byte = 0;
     const bool fast = s[0].c.bp + W3_LANE_FAST_MARGIN <= end_bits;
     for (uint32_t a = 0; a < 8u; a++) {
+      const uint32_t a1 = (a + 1u) & 7u;
       uint32_t bit[2];
-      for (uint32_t g = 0; g < 2; g++)
+      w3_pair_cand c[2];
+      for (uint32_t g = 0; g < 2; g++) { /* B then F then the repair, per lane, in the kernel's order */
+        const uint32_t khi0 = s[g].khi, klo0 = s[g].klo;
+        c[g] = w3_pair_guess(s[g], g, a1, m[g]);
         bit[g] = fast ? w3_pair_front<false>(s[g], m[g], ab, end_bits) : w3_pair_front<true>(s[g], m[g], ab, end_bits);
+        if (c[g].bad) w3_pair_repair(c[g], khi0, klo0, a1, m[g]);
+      }
       if (bit[0] != bit[1]) return -1;
-      const uint32_t ci = s[bit[0]].cci, P = s[bit[0]].cP;
-      for (uint32_t g = 0; g < 2; g++) {
-        s[g].ci = ci;
-        s[g].P = P;
-        w3_pair_back(s[g], g, (a + 2u) & 7u, m[g]);
+      for (uint32_t g = 0; g < 2; g++) { /* the pick */
+        s[g].ci = c[bit[0]].ci;
+        s[g].P = c[bit[0]].P;
       }
       byte = (byte << 1) | bit[0];
     }

@@ -46,6 +46,8 @@
  * memory: about one lookup in a hundred on text.
  */
 #pragma once
+#include <type_traits>
+
 #include "w3_core.cuh"
 
 #define W3_LANE_PB W3_PB2
@@ -267,27 +269,45 @@ W3_HD void w3_lane_decode_block(const uint8_t *sp, uint32_t slen, uint32_t n, ui
 }
 
 /* ---- pair form ----------------------------------------------------------------
- * Contexts of consecutive positions differ in their alignment bits, so a
- * candidate never reads a counter that the update in flight touches.  Written
- * as two halves around the pick so that tests/hostsim can run both lanes in
- * lockstep on the CPU. */
+ * Per bit t, from the state after bit t-1:
+ *   B  (lane g) candidate context and probability of position t+1 for the case bit t = g:
+ *      table lookup on the key with g shifted in, counter load, Counter::p;
+ *   F  (both lanes) decode bit t with the probability picked last time, adapt its counter,
+ *      shift it into the key;
+ *   pick: one shuffle pair takes the candidate of lane `bit t`.
+ * B and F are independent, so they are written back to back in ONE basic block and the
+ * scheduler interleaves their two chains (a lone warp issues in order: with the lookup after
+ * the coder step and a branch in between, as first written, a step cost the SUM of the two
+ * chains, 330 cycles).  The rare lane whose fixed lookup declined is repaired after F, behind
+ * one warp-uniform branch.  Contexts of consecutive positions differ in their alignment bits, so
+ * B never reads the counter F updates.  tests/hostsim runs both lanes in lockstep on the CPU. */
 struct w3_pair_dec {
   w3_lane_coder c;
   uint32_t khi, klo;
-  uint32_t ci, P;   /* counter offset and Counter::p << 16 of the bit being decoded (both lanes agree) */
-  uint32_t cci, cP; /* this lane's candidate for the next position: valid if the current bit equals its guess */
+  uint32_t ci, P; /* counter offset and Counter::p << 16 of the bit being decoded (both lanes agree) */
+};
+struct w3_pair_cand {
+  uint32_t ci, P; /* this lane's candidate for the next position: valid if the current bit equals its guess */
+  uint32_t gk;    /* the key's high word it was looked up with */
+  bool bad;       /* the fixed lookup declined: w3_pair_repair */
 };
 
-/* this lane's candidate for the position of alignment a2, assuming the next bit to be decoded is g */
-W3_HD void w3_pair_back(w3_pair_dec &s, uint32_t g, uint32_t a2, const w3_lane_mem &m) {
-  const uint32_t gk = (s.khi >> 1) | (g << 31);
-  bool bad;
-  uint32_t r = w3_lane_rank(gk, a2, m, bad);
-  if (bad) r = w3_lane_rank_slow(gk, w3_fsr(s.klo, s.khi, 1u), a2, m.g);
-  s.cci = ((r << W3_ALIGN_BITS) | a2) * 4u;
-  s.cP = w3_lane_P(w3_s_ld32(m.cnt + s.cci));
+/* B: this lane's candidate for the next position (alignment a1), assuming the bit about to be decoded is g */
+W3_HD w3_pair_cand w3_pair_guess(const w3_pair_dec &s, uint32_t g, uint32_t a1, const w3_lane_mem &m) {
+  w3_pair_cand c;
+  c.gk = (s.khi >> 1) | (g << 31);
+  const uint32_t r = w3_lane_rank(c.gk, a1, m, c.bad);
+  c.ci = ((r << W3_ALIGN_BITS) | a1) * 4u;
+  c.P = w3_lane_P(w3_s_ld32(m.cnt + c.ci)); /* of a wrong counter if bad: repaired below */
+  return c;
 }
-/* decode the current bit (main.rs:134-137 without the hash), both lanes alike */
+/* the general search for a candidate the fixed lookup declined; klo_before = the key's low word before F shifted it */
+W3_HD void w3_pair_repair(w3_pair_cand &c, uint32_t khi_before, uint32_t klo_before, uint32_t a1, const w3_lane_mem &m) {
+  const uint32_t r = w3_lane_rank_slow(c.gk, w3_fsr(klo_before, khi_before, 1u), a1, m.g);
+  c.ci = ((r << W3_ALIGN_BITS) | a1) * 4u;
+  c.P = w3_lane_P(w3_s_ld32(m.cnt + c.ci));
+}
+/* F: decode the current bit (main.rs:134-137 without the hash), both lanes alike */
 template <bool kCareful>
 W3_HD uint32_t w3_pair_front(w3_pair_dec &s, const w3_lane_mem &m, const uint32_t *ab, uint32_t end_bits) {
   const uint32_t bit = w3_lane_coder_step<kCareful>(s.c, s.P, ab, end_bits, m.ones);
@@ -325,7 +345,7 @@ __device__ __forceinline__ w3_lane_mem w3_lane_mem_of(w3_lane_tab *lt, uint32_t 
   return m;
 }
 
-__global__ void __launch_bounds__(W3_LANE_MAX_WARPS * 32u)
+__global__ void __launch_bounds__(W3_LANE_MAX_WARPS * 32u, 1)
 w3_decode_blocks_lane(const uint8_t *__restrict__ comp, const uint64_t *__restrict__ offsets, uint32_t n_blocks,
                       uint32_t block_size, uint64_t n_total, uint8_t *__restrict__ out, uint32_t *__restrict__ err,
                       const w3_hashtab *__restrict__ tab, uint32_t lanes) {
@@ -357,7 +377,7 @@ w3_decode_blocks_lane(const uint8_t *__restrict__ comp, const uint64_t *__restri
  * bytes' worth of steps; pairs beyond `pairs` and beyond the last block shadow a real pair of
  * the warp (same values, same stores), a short last block keeps stepping over its exhausted
  * stream without storing. */
-__global__ void __launch_bounds__(W3_LANE_MAX_WARPS * 32u)
+__global__ void __launch_bounds__(W3_LANE_MAX_WARPS * 32u, 1)
 w3_decode_blocks_pair(const uint8_t *__restrict__ comp, const uint64_t *__restrict__ offsets, uint32_t n_blocks,
                       uint32_t block_size, uint64_t n_total, uint8_t *__restrict__ out, uint32_t *__restrict__ err,
                       const w3_hashtab *__restrict__ tab, uint32_t pairs) {
@@ -392,31 +412,28 @@ w3_decode_blocks_pair(const uint8_t *__restrict__ comp, const uint64_t *__restri
     const w3_lane_mem m = w3_lane_mem_of(lt, counts + (warp * pairs + pair) * W3_NCTX, tab);
     w3_pair_dec s;
     w3_pair_init(s, ab, bp0, end_bits);
-    w3_pair_back(s, g, 1u, m);
     uint32_t word = 0;
     const uint32_t n_steps = block_size < n_total ? block_size : (uint32_t)n_total; /* the same for every lane */
+    auto step = [&](auto careful, uint32_t a1) -> uint32_t {
+      const uint32_t khi0 = s.khi, klo0 = s.klo;
+      w3_pair_cand c = w3_pair_guess(s, g, a1, m);                            /* B */
+      const uint32_t bit = w3_pair_front<decltype(careful)::value>(s, m, ab, end_bits); /* F */
+      if (__any_sync(0xFFFFFFFFu, c.bad)) {
+        if (c.bad) w3_pair_repair(c, khi0, klo0, a1, m);
+      }
+      const uint32_t src = (lane & 30u) | bit;                                /* pick */
+      s.ci = __shfl_sync(0xFFFFFFFFu, c.ci, src);
+      s.P = __shfl_sync(0xFFFFFFFFu, c.P, src);
+      return bit;
+    };
     for (uint32_t i = 0; i < n_steps; i++) {
       uint32_t byte = 0;
       if (__all_sync(0xFFFFFFFFu, s.c.bp + W3_LANE_FAST_MARGIN <= end_bits)) {
 #pragma unroll
-        for (uint32_t a = 0; a < 8u; a++) {
-          const uint32_t bit = w3_pair_front<false>(s, m, ab, end_bits);
-          const uint32_t src = (lane & 30u) | bit;
-          s.ci = __shfl_sync(0xFFFFFFFFu, s.cci, src);
-          s.P = __shfl_sync(0xFFFFFFFFu, s.cP, src);
-          w3_pair_back(s, g, (a + 2u) & 7u, m);
-          byte = (byte << 1) | bit;
-        }
+        for (uint32_t a = 0; a < 8u; a++) byte = (byte << 1) | step(std::false_type(), (a + 1u) & 7u);
       } else {
 #pragma unroll 1
-        for (uint32_t a = 0; a < 8u; a++) {
-          const uint32_t bit = w3_pair_front<true>(s, m, ab, end_bits);
-          const uint32_t src = (lane & 30u) | bit;
-          s.ci = __shfl_sync(0xFFFFFFFFu, s.cci, src);
-          s.P = __shfl_sync(0xFFFFFFFFu, s.cP, src);
-          w3_pair_back(s, g, (a + 2u) & 7u, m);
-          byte = (byte << 1) | bit;
-        }
+        for (uint32_t a = 0; a < 8u; a++) byte = (byte << 1) | step(std::true_type(), (a + 1u) & 7u);
       }
       word |= byte << (8u * (i & 3u));
       if ((i & 3u) == 3u) {
