@@ -160,6 +160,18 @@ void w3o_slot_set_nib(uint8_t cell[96], int id, uint8_t nib, const uint16_t s[4]
 void w3o_slot_get_nib(const uint8_t cell[96], int id, uint8_t nib, uint16_t s[4]); /* :121-128 */
 uint16_t w3o_opinion_mix2(uint16_t p1, uint16_t p2); /* OpinionMixer2::mix — src/mixers/opinion_mixer2.rs:5-10 */
 
+/* ---- Tier C: the hashed context-mixing stack "w3cm" (w3_cm_oracle.c) -----
+ * PARITY UNPINNED by the reference (it has no logistic mixer, no APM, no caller of its hash map
+ * or state table): w3_cm_oracle.c is the specification.  Judged on round trip and on identity of
+ * the GPU path with this oracle. */
+int w3o_cm_squash(int d);            /* 12-bit logistic, d in 1/256 units */
+int w3o_cm_stretch(int p);           /* its inverse table */
+int w3o_cm_state_bits(uint16_t s);   /* bits a state has seen (replacement policy) */
+uint64_t w3o_cm_hash(uint64_t last8, int model, int low_nibble, unsigned hi);
+int w3o_cm_find_slot(uint8_t cell[96], uint64_t hash); /* Cell::get_slot + replacement */
+int w3o_cm_compress_block(const uint8_t *in, size_t n, int log_cells, uint8_t *out, size_t cap, size_t *out_len);
+int w3o_cm_decompress_block(const uint8_t *in, size_t n_in, int log_cells, uint8_t *out, size_t n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -98,6 +98,13 @@ def load_oracle():
     o.w3o_slot_get_nib.argtypes = [C.c_void_p, C.c_int, C.c_uint8, u16p]
     o.w3o_opinion_mix2.restype = C.c_uint16
     o.w3o_opinion_mix2.argtypes = [C.c_uint16, C.c_uint16]
+    o.w3o_cm_squash.argtypes = o.w3o_cm_stretch.argtypes = [C.c_int]
+    o.w3o_cm_state_bits.argtypes = [C.c_uint16]
+    o.w3o_cm_hash.restype = C.c_uint64
+    o.w3o_cm_hash.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_uint]
+    o.w3o_cm_find_slot.argtypes = [C.c_void_p, C.c_uint64]
+    o.w3o_cm_compress_block.argtypes = [u8p, sz, C.c_int, C.c_void_p, sz, C.POINTER(sz)]
+    o.w3o_cm_decompress_block.argtypes = [u8p, sz, C.c_int, C.c_void_p, sz]
     o.w3o_compress_blocks_mt.argtypes = [C.c_void_p, sz, sz, C.c_void_p, sz, C.c_void_p, C.c_int]
     o.w3o_decompress_blocks_mt.argtypes = [C.c_void_p, sz, C.c_void_p, C.c_void_p, sz, sz, C.c_int]
     return o
@@ -150,6 +157,21 @@ class Oracle:
         rc = self.lib.w3o_sweep_exec(data, len(data), t, ctx_bits, align_bits, C.byref(bc))
         assert rc == 0, rc
         return bc.value
+
+    def cm_compress_block(self, data: bytes, log_cells: int = 16) -> bytes:
+        n = len(data)
+        cap = 2 * n + 64
+        out = C.create_string_buffer(cap)
+        ol = C.c_size_t()
+        rc = self.lib.w3o_cm_compress_block(data, n, log_cells, out, cap, C.byref(ol))
+        assert rc == 0, rc
+        return out.raw[: ol.value]
+
+    def cm_decompress_block(self, stream: bytes, n_out: int, log_cells: int = 16) -> bytes:
+        out = C.create_string_buffer(max(n_out, 1))
+        rc = self.lib.w3o_cm_decompress_block(stream, len(stream), log_cells, out, n_out)
+        assert rc == 0, rc
+        return out.raw[:n_out]
 
     def stationary_new(self, data: bytes):
         t = (C.c_uint16 * 8)()
@@ -234,8 +256,8 @@ class HostSim:
         h.hs_slot_get_nib.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint16)]
         h.hs_cell_index.restype = C.c_uint64
         h.hs_cell_index.argtypes = [C.c_uint64, C.c_uint32]
-        h.hs_lane_decode_block.argtypes = [C.c_void_p, C.c_char_p, sz, C.c_uint, C.c_uint8, C.c_void_p, sz]
-        h.hs_pair_decode_block.argtypes = [C.c_void_p, C.c_char_p, sz, C.c_uint, C.c_uint8, C.c_void_p, sz]
+        h.hs_lane_decode_block.argtypes = [C.c_void_p, C.c_char_p, sz, C.c_uint, C.c_uint8, C.c_void_p, sz, C.c_int]
+        h.hs_pair_decode_block.argtypes = [C.c_void_p, C.c_char_p, sz, C.c_uint, C.c_uint8, C.c_void_p, sz, C.c_int]
         self.lib = h
         self.table = (C.c_uint16 * 8)(*table)
         self.max_bits = max_bits
@@ -264,12 +286,13 @@ class HostSim:
         self.lib.hs_decompress_block(self.tab, stream, len(stream), out, n_out)
         return out.raw[:n_out]
 
-    def lane_decode_block(self, stream: bytes, n_out: int, misalign: int = 0, junk: int = 0xA5, pair: bool = False) -> bytes:
+    def lane_decode_block(self, stream: bytes, n_out: int, misalign: int = 0, junk: int = 0xA5, pair=False) -> bytes:
         """w3_lane.cuh's per-lane decoder (what w3_decode_blocks_lane runs in every lane), or its
-        pair form (w3_decode_blocks_pair: two lanes per block in lockstep)."""
+        pair form (w3_decode_blocks_pair: two lanes per block in lockstep; pair="cache" = with the
+        probability table)."""
         out = C.create_string_buffer(max(n_out, 1))
         fn = self.lib.hs_pair_decode_block if pair else self.lib.hs_lane_decode_block
-        rc = fn(self.tab, stream, len(stream), misalign, junk, out, n_out)
+        rc = fn(self.tab, stream, len(stream), misalign, junk, out, n_out, 1 if pair == "cache" else 0)
         assert rc == 0, rc
         return out.raw[:n_out]
 

@@ -236,7 +236,7 @@ struct hs_lane_env {
   }
 };
 int hs_lane_decode_block(const w3_hashtab *tab, const uint8_t *in, size_t n_in, unsigned misalign,
-                         uint8_t junk, uint8_t *out, size_t n_out) {
+                         uint8_t junk, uint8_t *out, size_t n_out, int /*unused*/) {
   hs_lane_env env(tab, in, n_in, misalign, junk);
   std::vector<uint32_t> cnt(W3_NCTX, 0u);
   std::vector<uint32_t> dst((n_out + 3) / 4 + 1, 0u);
@@ -249,39 +249,57 @@ int hs_lane_decode_block(const w3_hashtab *tab, const uint8_t *in, size_t n_in, 
 /* the pair form of the lane decoder: both lanes of a pair in lockstep, the pick (a shuffle on the
  * device) done by hand.  Each lane applies the (identical) counter update, as on the device; so
  * that lane 1's does not see lane 0's, each has its own copy, and they must stay equal. */
-int hs_pair_decode_block(const w3_hashtab *tab, const uint8_t *in, size_t n_in, unsigned misalign,
-                         uint8_t junk, uint8_t *out, size_t n_out) {
+} /* extern "C" */
+template <bool kCacheP>
+static int hs_pair_decode(const w3_hashtab *tab, const uint8_t *in, size_t n_in, unsigned misalign,
+                          uint8_t junk, uint8_t *out, size_t n_out) {
   hs_lane_env env(tab, in, n_in, misalign, junk);
   const uint32_t sh = (uint32_t)((uintptr_t)env.sp & 3u);
   const uint32_t *ab = (const uint32_t *)(env.sp - sh);
   const uint32_t bp0 = sh * 8u, end_bits = bp0 + (uint32_t)n_in * 8u;
-  std::vector<uint32_t> cnt0(W3_NCTX, 0u), cnt1(W3_NCTX, 0u);
+  const size_t words = kCacheP ? 2 * W3_NCTX : W3_NCTX;
+  std::vector<uint32_t> cnt0(words, 0u), cnt1(words, 0u);
+  if (kCacheP)
+    for (size_t i = W3_NCTX; i < words; i++) cnt0[i] = cnt1[i] = 0x80000000u;
   const w3_lane_mem m[2] = {env.mem(cnt0.data(), tab), env.mem(cnt1.data(), tab)};
   w3_pair_dec s[2];
-  for (uint32_t g = 0; g < 2; g++) w3_pair_init(s[g], ab, bp0, end_bits);
+  w3_pair_cand cand[2];
+  for (uint32_t g = 0; g < 2; g++) {
+    w3_pair_init(s[g], ab, bp0, end_bits);
+    cand[g] = w3_pair_guess<kCacheP>(s[g], g, 1u, m[g]);
+  }
   for (size_t i = 0; i < n_out; i++) {
     uint32_t byte = 0;
     const bool fast = s[0].c.bp + W3_LANE_FAST_MARGIN <= end_bits;
     for (uint32_t a = 0; a < 8u; a++) {
-      const uint32_t a1 = (a + 1u) & 7u;
       uint32_t bit[2];
-      w3_pair_cand c[2];
-      for (uint32_t g = 0; g < 2; g++) { /* B then F then the repair, per lane, in the kernel's order */
-        const uint32_t khi0 = s[g].khi, klo0 = s[g].klo;
-        c[g] = w3_pair_guess(s[g], g, a1, m[g]);
-        bit[g] = fast ? w3_pair_front<false>(s[g], m[g], ab, end_bits) : w3_pair_front<true>(s[g], m[g], ab, end_bits);
-        if (c[g].bad) w3_pair_repair(c[g], khi0, klo0, a1, m[g]);
+      for (uint32_t g = 0; g < 2; g++) { /* F, then the late repair, per lane, in the kernel's order */
+        bit[g] = fast ? w3_pair_front<false, kCacheP>(s[g], m[g], ab, end_bits)
+                      : w3_pair_front<true, kCacheP>(s[g], m[g], ab, end_bits);
+        if (cand[g].bad) w3_pair_repair<kCacheP>(cand[g], (a + 1u) & 7u, m[g]);
       }
       if (bit[0] != bit[1]) return -1;
-      for (uint32_t g = 0; g < 2; g++) { /* the pick */
-        s[g].ci = c[bit[0]].ci;
-        s[g].P = c[bit[0]].P;
+      const uint32_t ci = cand[bit[0]].ci, P = cand[bit[0]].P; /* the pick */
+      for (uint32_t g = 0; g < 2; g++) {
+        s[g].ci = ci;
+        s[g].P = P;
+        cand[g] = w3_pair_guess<kCacheP>(s[g], g, (a + 2u) & 7u, m[g]); /* B */
       }
       byte = (byte << 1) | bit[0];
     }
     out[i] = (uint8_t)byte;
   }
   return cnt0 == cnt1 ? 0 : -2;
+}
+extern "C" {
+/* the pair form of the lane decoder: both lanes of a pair in lockstep, the pick (a shuffle on the
+ * device) done by hand.  Each lane applies the (identical) counter update, as on the device; so
+ * that lane 1's does not see lane 0's, each has its own copy, and they must stay equal.
+ * cache_p: the variant with the probability table (w3_decode_blocks_pair<true>). */
+int hs_pair_decode_block(const w3_hashtab *tab, const uint8_t *in, size_t n_in, unsigned misalign,
+                         uint8_t junk, uint8_t *out, size_t n_out, int cache_p) {
+  return cache_p ? hs_pair_decode<true>(tab, in, n_in, misalign, junk, out, n_out)
+                 : hs_pair_decode<false>(tab, in, n_in, misalign, junk, out, n_out);
 }
 
 /* ---- w3_tierb.cuh on the CPU -------------------------------------------------------------- */

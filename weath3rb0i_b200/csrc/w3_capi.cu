@@ -272,7 +272,7 @@ int w3_ctx_set_option(w3_ctx *ctx, int option, int value) {
     case W3_OPT_KERNELS: if (value > 3) return W3_E_ARG; ctx->opts.kernels = value; return W3_OK;
     case W3_OPT_ENC_TEAMS: if (value > 8) return W3_E_ARG; ctx->opts.enc_teams = value; return W3_OK;
     case W3_OPT_LANE_WARPS: if (value > 8) return W3_E_ARG; ctx->opts.lane_warps = value; return W3_OK;
-    case W3_OPT_LANE_FORM: if (value > 2) return W3_E_ARG; ctx->opts.lane_form = value; return W3_OK;
+    case W3_OPT_LANE_FORM: if (value > 3) return W3_E_ARG; ctx->opts.lane_form = value; return W3_OK;
     default: return W3_E_ARG;
   }
 }

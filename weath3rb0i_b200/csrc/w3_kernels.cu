@@ -675,8 +675,11 @@ cudaError_t w3_kernels_init(void) {
   e = cudaFuncSetAttribute(w3_decode_blocks_lane, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)(sizeof(w3_lane_tab) + w3_lane_cap() * W3_NCTX * 4u));
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(w3_decode_blocks_pair, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = cudaFuncSetAttribute(w3_decode_blocks_pair<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)(sizeof(w3_lane_tab) + w3_lane_cap() * W3_NCTX * 4u));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(w3_decode_blocks_pair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(sizeof(w3_lane_tab) + (w3_lane_cap() / 2u) * W3_NCTX * 8u));
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(w3_k_hash_array, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)sizeof(w3_smem_tab));
@@ -746,21 +749,30 @@ cudaError_t w3_launch_decode(const uint8_t *d_comp, const uint64_t *d_offsets, u
   }
   /* lanes: `resident` blocks per CTA at a time, spread over `warps` warps (one per SM
    * sub-partition by default) of `lanes` blocks each; the pair form (two lanes per block, the next
-   * position's lookup overlapping the current bit's coder step) unless the lane form is asked for */
-  const uint32_t per = w3_per_cta(n_blocks, sm_count, w3_lane_cap());
+   * position's lookup overlapping the current bit's coder step) unless the lane form is asked for.
+   * While all of an SM's blocks fit with 16 KiB each, the pair form keeps Counter::p of every
+   * counter in a second table (the chain per bit is what a step costs then); beyond that,
+   * residency matters more and the probability is recomputed from the counts. */
+  const int form = opts ? opts->lane_form : 0;
+  const uint32_t q = w3_ceil_div(n_blocks, (uint32_t)sm_count);
+  const bool pair = form != 1;
+  const bool cache_p = pair && (form == 3 || (form == 0 && q <= w3_lane_cap() / 2u));
+  const uint32_t cap = cache_p ? w3_lane_cap() / 2u : w3_lane_cap();
+  const uint32_t per = w3_per_cta(n_blocks, sm_count, cap);
   uint32_t warps = per < 4u ? per : 4u;
   if (opts && opts->lane_warps > 0) warps = (uint32_t)opts->lane_warps < W3_LANE_MAX_WARPS ? (uint32_t)opts->lane_warps : W3_LANE_MAX_WARPS;
   if (warps > per) warps = per;
   uint32_t lanes = w3_ceil_div(per, warps);
-  while (warps * lanes > w3_lane_cap()) lanes--; /* rounding up may overshoot what fits */
-  const bool pair = !(opts && opts->lane_form == 1);
+  while (warps * lanes > cap) lanes--; /* rounding up may overshoot what fits */
   if (pair && lanes > 16u) lanes = 16u;
   const uint32_t resident = warps * lanes;
   uint32_t grid = w3_ceil_div(n_blocks, resident);
   if (grid > (uint32_t)sm_count) grid = (uint32_t)sm_count;
-  const size_t smem = sizeof(w3_lane_tab) + (size_t)resident * W3_NCTX * 4u;
-  if (pair)
-    w3_decode_blocks_pair<<<grid, warps * 32u, smem, s>>>(d_comp, d_offsets, n_blocks, block_size, n_total, d_out, d_err, d_tab, lanes);
+  const size_t smem = sizeof(w3_lane_tab) + (size_t)resident * W3_NCTX * (cache_p ? 8u : 4u);
+  if (cache_p)
+    w3_decode_blocks_pair<true><<<grid, warps * 32u, smem, s>>>(d_comp, d_offsets, n_blocks, block_size, n_total, d_out, d_err, d_tab, lanes);
+  else if (pair)
+    w3_decode_blocks_pair<false><<<grid, warps * 32u, smem, s>>>(d_comp, d_offsets, n_blocks, block_size, n_total, d_out, d_err, d_tab, lanes);
   else
     w3_decode_blocks_lane<<<grid, warps * 32u, smem, s>>>(d_comp, d_offsets, n_blocks, block_size, n_total, d_out, d_err, d_tab, lanes);
   return cudaGetLastError();

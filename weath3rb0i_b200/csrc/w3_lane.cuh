@@ -269,49 +269,65 @@ W3_HD void w3_lane_decode_block(const uint8_t *sp, uint32_t slen, uint32_t n, ui
 }
 
 /* ---- pair form ----------------------------------------------------------------
- * Per bit t, from the state after bit t-1:
- *   B  (lane g) candidate context and probability of position t+1 for the case bit t = g:
- *      table lookup on the key with g shifted in, counter load, Counter::p;
- *   F  (both lanes) decode bit t with the probability picked last time, adapt its counter,
- *      shift it into the key;
- *   pick: one shuffle pair takes the candidate of lane `bit t`.
- * B and F are independent, so they are written back to back in ONE basic block and the
- * scheduler interleaves their two chains (a lone warp issues in order: with the lookup after
- * the coder step and a branch in between, as first written, a step cost the SUM of the two
- * chains, 330 cycles).  The rare lane whose fixed lookup declined is repaired after F, behind
- * one warp-uniform branch.  Contexts of consecutive positions differ in their alignment bits, so
- * B never reads the counter F updates.  tests/hostsim runs both lanes in lockstep on the CPU. */
+ * Per bit t:
+ *   F     (both lanes) decode bit t with the probability picked last time, adapt its
+ *         counter, shift the bit into the key;
+ *   pick  one shuffle pair takes the candidate (context, probability) of position t+1
+ *         from the lane whose guess of bit t came true;
+ *   B     (lane g) candidate for position t+2 for the case bit t+1 = g: table lookup on
+ *         the key with g shifted in, then the probability of that context.
+ * B of bit t and F of bit t+1 are independent and sit in ONE basic block, so the scheduler
+ * interleaves the two chains (a lone warp issues in order: with a branch between them a step
+ * costs the sum of the chains).  Hence the rare lane whose fixed lookup declined is repaired
+ * late — just before its candidate is picked, behind one warp-uniform branch.
+ * kCacheP: a second table per block holds Counter::p << 16 of every counter, kept current by
+ * F (off the chain), so that B ends with one load instead of a division: the chain from
+ * "bit known" to "candidate ready" is what a step costs when few blocks share an SM.
+ * Contexts of consecutive positions differ in their alignment bits, so B never touches a
+ * counter F updates in the same or the next step.  tests/hostsim runs both lanes in
+ * lockstep on the CPU. */
 struct w3_pair_dec {
   w3_lane_coder c;
   uint32_t khi, klo;
   uint32_t ci, P; /* counter offset and Counter::p << 16 of the bit being decoded (both lanes agree) */
 };
 struct w3_pair_cand {
-  uint32_t ci, P; /* this lane's candidate for the next position: valid if the current bit equals its guess */
-  uint32_t gk;    /* the key's high word it was looked up with */
-  bool bad;       /* the fixed lookup declined: w3_pair_repair */
+  uint32_t ci, P;   /* this lane's candidate for the position after next: valid if the next bit equals its guess */
+  uint32_t gk, glo; /* the key it was looked up with */
+  bool bad;         /* the fixed lookup declined: w3_pair_repair before the pick */
 };
+#define W3_LANE_P_OFF (W3_NCTX * 4u) /* kCacheP: byte offset of the probability table behind a block's counters */
 
-/* B: this lane's candidate for the next position (alignment a1), assuming the bit about to be decoded is g */
-W3_HD w3_pair_cand w3_pair_guess(const w3_pair_dec &s, uint32_t g, uint32_t a1, const w3_lane_mem &m) {
+template <bool kCacheP>
+W3_HD uint32_t w3_pair_P_of(uint32_t ci, const w3_lane_mem &m) {
+  return kCacheP ? w3_s_ld32(m.cnt + W3_LANE_P_OFF + ci) : w3_lane_P(w3_s_ld32(m.cnt + ci));
+}
+/* B: this lane's candidate for the position of alignment a2, assuming the next bit to be decoded is g */
+template <bool kCacheP>
+W3_HD w3_pair_cand w3_pair_guess(const w3_pair_dec &s, uint32_t g, uint32_t a2, const w3_lane_mem &m) {
   w3_pair_cand c;
   c.gk = (s.khi >> 1) | (g << 31);
-  const uint32_t r = w3_lane_rank(c.gk, a1, m, c.bad);
-  c.ci = ((r << W3_ALIGN_BITS) | a1) * 4u;
-  c.P = w3_lane_P(w3_s_ld32(m.cnt + c.ci)); /* of a wrong counter if bad: repaired below */
+  c.glo = w3_fsr(s.klo, s.khi, 1u);
+  const uint32_t r = w3_lane_rank(c.gk, a2, m, c.bad);
+  c.ci = (((r & 255u) << W3_ALIGN_BITS) | a2) * 4u; /* r <= 255 unless bad: the load below stays inside the table */
+  c.P = w3_pair_P_of<kCacheP>(c.ci, m);             /* of a wrong counter if bad: repaired before the pick */
   return c;
 }
-/* the general search for a candidate the fixed lookup declined; klo_before = the key's low word before F shifted it */
-W3_HD void w3_pair_repair(w3_pair_cand &c, uint32_t khi_before, uint32_t klo_before, uint32_t a1, const w3_lane_mem &m) {
-  const uint32_t r = w3_lane_rank_slow(c.gk, w3_fsr(klo_before, khi_before, 1u), a1, m.g);
-  c.ci = ((r << W3_ALIGN_BITS) | a1) * 4u;
-  c.P = w3_lane_P(w3_s_ld32(m.cnt + c.ci));
+/* the general search for a candidate the fixed lookup declined */
+template <bool kCacheP>
+W3_HD void w3_pair_repair(w3_pair_cand &c, uint32_t a2, const w3_lane_mem &m) {
+  const uint32_t r = w3_lane_rank_slow(c.gk, c.glo, a2, m.g);
+  c.ci = ((r << W3_ALIGN_BITS) | a2) * 4u;
+  c.P = w3_pair_P_of<kCacheP>(c.ci, m);
+  c.bad = false;
 }
 /* F: decode the current bit (main.rs:134-137 without the hash), both lanes alike */
-template <bool kCareful>
+template <bool kCareful, bool kCacheP>
 W3_HD uint32_t w3_pair_front(w3_pair_dec &s, const w3_lane_mem &m, const uint32_t *ab, uint32_t end_bits) {
   const uint32_t bit = w3_lane_coder_step<kCareful>(s.c, s.P, ab, end_bits, m.ones);
-  w3_s_st32(m.cnt + s.ci, w3_counter_update(w3_s_ld32(m.cnt + s.ci), bit)); /* both lanes store the same word */
+  const uint32_t nv = w3_counter_update(w3_s_ld32(m.cnt + s.ci), bit);
+  w3_s_st32(m.cnt + s.ci, nv); /* both lanes store the same words */
+  if (kCacheP) w3_s_st32(m.cnt + W3_LANE_P_OFF + s.ci, w3_lane_P(nv));
   s.klo = w3_fsr(s.klo, s.khi, 1u);
   s.khi = (s.khi >> 1) | (bit << 31);
   return bit;
@@ -377,6 +393,7 @@ w3_decode_blocks_lane(const uint8_t *__restrict__ comp, const uint64_t *__restri
  * bytes' worth of steps; pairs beyond `pairs` and beyond the last block shadow a real pair of
  * the warp (same values, same stores), a short last block keeps stepping over its exhausted
  * stream without storing. */
+template <bool kCacheP>
 __global__ void __launch_bounds__(W3_LANE_MAX_WARPS * 32u, 1)
 w3_decode_blocks_pair(const uint8_t *__restrict__ comp, const uint64_t *__restrict__ offsets, uint32_t n_blocks,
                       uint32_t block_size, uint64_t n_total, uint8_t *__restrict__ out, uint32_t *__restrict__ err,
@@ -387,11 +404,13 @@ w3_decode_blocks_pair(const uint8_t *__restrict__ comp, const uint64_t *__restri
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   const uint32_t per_cta = (blockDim.x >> 5) * pairs;
   const uint32_t g = lane & 1u;
+  const uint32_t words = kCacheP ? 2u * W3_NCTX : W3_NCTX; /* per block: counters (+ probabilities) */
 
   w3_lane_stage(lt, tab);
   for (uint32_t first = blockIdx.x * per_cta; first < n_blocks; first += gridDim.x * per_cta) {
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < per_cta * W3_NCTX; i += blockDim.x) counts[i] = 0u;
+    for (uint32_t i = threadIdx.x; i < per_cta * words; i += blockDim.x)
+      counts[i] = (kCacheP && (i % words) >= W3_NCTX) ? 0x80000000u : 0u; /* Counter::new: counts 0, p = 32768 */
     __syncthreads();
     const uint32_t wfirst = first + warp * pairs; /* this warp's first block */
     if (wfirst >= n_blocks) continue;              /* warp-uniform */
@@ -409,31 +428,31 @@ w3_decode_blocks_pair(const uint8_t *__restrict__ comp, const uint64_t *__restri
     const uint32_t sh = (uint32_t)((uintptr_t)sp & 3u);
     const uint32_t *ab = (const uint32_t *)(sp - sh);
     const uint32_t bp0 = sh * 8u, end_bits = bp0 + (uint32_t)slen * 8u;
-    const w3_lane_mem m = w3_lane_mem_of(lt, counts + (warp * pairs + pair) * W3_NCTX, tab);
+    const w3_lane_mem m = w3_lane_mem_of(lt, counts + (warp * pairs + pair) * words, tab);
     w3_pair_dec s;
     w3_pair_init(s, ab, bp0, end_bits);
+    w3_pair_cand cand = w3_pair_guess<kCacheP>(s, g, 1u, m); /* position 1, for either value of bit 0 */
     uint32_t word = 0;
     const uint32_t n_steps = block_size < n_total ? block_size : (uint32_t)n_total; /* the same for every lane */
-    auto step = [&](auto careful, uint32_t a1) -> uint32_t {
-      const uint32_t khi0 = s.khi, klo0 = s.klo;
-      w3_pair_cand c = w3_pair_guess(s, g, a1, m);                            /* B */
-      const uint32_t bit = w3_pair_front<decltype(careful)::value>(s, m, ab, end_bits); /* F */
-      if (__any_sync(0xFFFFFFFFu, c.bad)) {
-        if (c.bad) w3_pair_repair(c, khi0, klo0, a1, m);
+    auto step = [&](auto careful, uint32_t a) -> uint32_t {
+      const uint32_t bit = w3_pair_front<decltype(careful)::value, kCacheP>(s, m, ab, end_bits); /* F */
+      if (__any_sync(0xFFFFFFFFu, cand.bad)) {
+        if (cand.bad) w3_pair_repair<kCacheP>(cand, (a + 1u) & 7u, m);
       }
-      const uint32_t src = (lane & 30u) | bit;                                /* pick */
-      s.ci = __shfl_sync(0xFFFFFFFFu, c.ci, src);
-      s.P = __shfl_sync(0xFFFFFFFFu, c.P, src);
+      const uint32_t src = (lane & 30u) | bit;                                                   /* pick */
+      s.ci = __shfl_sync(0xFFFFFFFFu, cand.ci, src);
+      s.P = __shfl_sync(0xFFFFFFFFu, cand.P, src);
+      cand = w3_pair_guess<kCacheP>(s, g, (a + 2u) & 7u, m);                                     /* B */
       return bit;
     };
     for (uint32_t i = 0; i < n_steps; i++) {
       uint32_t byte = 0;
       if (__all_sync(0xFFFFFFFFu, s.c.bp + W3_LANE_FAST_MARGIN <= end_bits)) {
 #pragma unroll
-        for (uint32_t a = 0; a < 8u; a++) byte = (byte << 1) | step(std::false_type(), (a + 1u) & 7u);
+        for (uint32_t a = 0; a < 8u; a++) byte = (byte << 1) | step(std::false_type(), a);
       } else {
 #pragma unroll 1
-        for (uint32_t a = 0; a < 8u; a++) byte = (byte << 1) | step(std::true_type(), (a + 1u) & 7u);
+        for (uint32_t a = 0; a < 8u; a++) byte = (byte << 1) | step(std::true_type(), a);
       }
       word |= byte << (8u * (i & 3u));
       if ((i & 3u) == 3u) {
