@@ -111,6 +111,21 @@ typedef struct w3_sweep_point {
 int w3_sweep(w3_ctx *ctx, const uint8_t *in, size_t n, const uint16_t table[8], const w3_sweep_point *points,
              size_t n_points, uint64_t *bit_counts, uint16_t table_used[8]);
 
+/* ---- the hashed context-mixing stack "w3cm" ----------------------------------
+ * What BASELINE.json's north star describes and the reference only plans (README.md:6-10):
+ * six hashed contexts per nibble in the reference's cell / slot layout (src/hashmap.rs,
+ * docs/hashslots.md), bit histories through its 12-bit state table (src/state_table/naive.rs), a
+ * logistic mixer, an APM, and the reference's arithmetic coder.  The reference has no such model
+ * (no mixer, no APM, no caller of its hash map): there is nothing to be byte-identical to, the
+ * specification is oracle/w3_cm_oracle.c and parity means identity with that oracle.
+ * One warp per block, lanes = models; every block has its own table of 2^log_cells 96-byte cells
+ * in HBM (log_cells 4..24).  Container:
+ *   "w3Cm" | u8 1 | u8 models (6) | u8 log_cells | u8 0 | u64 BE n | u32 BE block_size | u32 BE n_blocks
+ *   | n_blocks x u32 BE stream length | streams */
+int w3_cm_compress(w3_ctx *ctx, const uint8_t *in, size_t n, size_t block_size, int log_cells, uint8_t *out,
+                   size_t cap, size_t *out_len);
+int w3_cm_decompress(w3_ctx *ctx, const uint8_t *in, size_t n_in, uint8_t *out, size_t cap, size_t *out_len);
+
 /* Upper bound of w3_compress output for n input bytes. */
 size_t w3_compress_bound(size_t n, size_t block_size);
 

@@ -10,9 +10,13 @@ if [ "$1" = build ]; then
   for v in "$@"; do
     name=${v%%:*}; flags=${v#*:}
     nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall $flags \
-      -shared -o tools/variants/$name.so weath3rb0i_b200/csrc/w3_kernels.cu weath3rb0i_b200/csrc/w3_capi.cu 2>&1 | grep -E "error" &
+      -shared -o tools/variants/$name.so weath3rb0i_b200/csrc/w3_kernels.cu weath3rb0i_b200/csrc/w3_tierb.cu weath3rb0i_b200/csrc/w3_geo.cu weath3rb0i_b200/csrc/w3_capi.cu 2>&1 | grep -E "error" &
   done
   wait; ls tools/variants
+elif [ "$1" = many ]; then
+  # scripts/variants.sh many MIB BLOCK_KIB cfg...: the many-block experiment harness on every variant
+  shift
+  for so in tools/variants/*.so; do echo "== $(basename $so .so)"; W3_LIB=$PWD/$so timeout 300 python scripts/exp_many.py "$@" 2>&1 | tail -n +2; done
 elif [ "$1" = dec ]; then
   for so in tools/variants/*.so; do W3_LIB=$PWD/$so timeout 120 python scripts/exp_decode.py 2>&1 | tail -2; done
 else

@@ -256,6 +256,11 @@ class HostSim:
         h.hs_slot_get_nib.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint16)]
         h.hs_cell_index.restype = C.c_uint64
         h.hs_cell_index.argtypes = [C.c_uint64, C.c_uint32]
+        h.hs_cm_hash.restype = C.c_uint64
+        h.hs_cm_hash.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
+        h.hs_cm_find_slot.argtypes = [C.c_void_p, C.c_uint64]
+        h.hs_cm_squash.argtypes = h.hs_cm_stretch.argtypes = [C.c_int]
+        h.hs_cm_train.argtypes = [C.c_int32, C.c_int, C.c_int]
         h.hs_lane_decode_block.argtypes = [C.c_void_p, C.c_char_p, sz, C.c_uint, C.c_uint8, C.c_void_p, sz, C.c_int]
         h.hs_pair_decode_block.argtypes = [C.c_void_p, C.c_char_p, sz, C.c_uint, C.c_uint8, C.c_void_p, sz, C.c_int]
         self.lib = h

@@ -12,6 +12,7 @@
 #include "../../weath3rb0i_b200/csrc/w3_core.cuh"
 #include "../../weath3rb0i_b200/csrc/w3_lane.cuh"
 #include "../../weath3rb0i_b200/csrc/w3_tierb.cuh"
+#include "../../weath3rb0i_b200/csrc/w3_cm.cuh"
 
 extern "C" {
 
@@ -315,5 +316,14 @@ void hs_slot_set_nib(uint8_t *cell, uint32_t id, uint32_t nib, const uint16_t *s
 void hs_slot_get_nib(const uint8_t *cell, uint32_t id, uint32_t nib, uint16_t *s) { w3_slot_get_nib(cell, id, nib, s); }
 uint64_t hs_cell_index(uint64_t hash, uint32_t log_cell_count) { return w3_cell_index(hash, log_cell_count); }
 uint32_t hs_opinion_mix2(uint32_t p1, uint32_t p2) { return w3_opinion_mix2(p1, p2); }
+
+/* ---- w3_cm.cuh on the CPU ----------------------------------------------------------------- */
+static const int16_t HS_SQ33[33] = W3_CM_SQ33;
+int hs_cm_squash(int d) { return w3_cm_squash(d, HS_SQ33); }
+int hs_cm_stretch(int p) { return w3_cm_stretch_entry(p, HS_SQ33); }
+uint32_t hs_cm_state_bits(uint32_t s) { return w3_cm_state_bits(s); }
+uint64_t hs_cm_hash(uint64_t last8, uint32_t model, uint32_t low, uint32_t hi) { return w3_cm_hash(last8, model, low, hi); }
+uint32_t hs_cm_find_slot(uint8_t *cell, uint64_t hash) { return w3_cm_find_slot(cell, hash, nullptr); }
+int32_t hs_cm_train(int32_t w, int st, int err) { return w3_cm_train(w, st, err); }
 
 } /* extern "C" */

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libw3codec.so")
 CLI = os.path.join(HERE, "w3")
-SOURCES = ["w3_kernels.cu", "w3_tierb.cu", "w3_geo.cu", "w3_capi.cu"]
+SOURCES = ["w3_kernels.cu", "w3_tierb.cu", "w3_geo.cu", "w3_cm.cu", "w3_capi.cu"]
 DEPS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))) + [
     os.path.join("..", "..", "include", "w3_codec.h")
 ]

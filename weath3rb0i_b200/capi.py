@@ -21,7 +21,7 @@ DEFAULT_BLOCK = 1 << 20
 SYMBOLS = (
     "w3_ctx_create", "w3_ctx_destroy", "w3_ctx_device_count", "w3_ctx_set_option", "w3_compress_bound",
     "w3_ctx_set_model", "w3_ctx_get_model", "w3_train_model", "w3_ctx_set_geometry", "w3_ctx_get_geometry", "w3_sweep",
-    "w3_compress", "w3_decompress", "w3_decompress_blocks", "w3_decompressed_size",
+    "w3_compress", "w3_decompress", "w3_decompress_blocks", "w3_decompressed_size", "w3_cm_compress", "w3_cm_decompress",
     "w3_encode_device", "w3_pack_device", "w3_decode_device",
     "w3_selftest_achash", "w3_selftest_counter_p", "w3_probe_sector_gather", "w3_selftest_ac_encode", "w3_selftest_ac_decode",
     "w3_selftest_state_table", "w3_selftest_hashslots",
@@ -70,6 +70,8 @@ def load():
     lib.w3_decompress.argtypes = [vp, u8p, sz, u8p, sz, C.POINTER(sz)]
     lib.w3_decompress_blocks.argtypes = [vp, u8p, sz, sz, sz, u8p, sz, C.POINTER(sz)]
     lib.w3_decompressed_size.argtypes = [u8p, sz, C.POINTER(sz)]
+    lib.w3_cm_compress.argtypes = [vp, u8p, sz, sz, C.c_int, u8p, sz, C.POINTER(sz)]
+    lib.w3_cm_decompress.argtypes = [vp, u8p, sz, u8p, sz, C.POINTER(sz)]
     lib.w3_encode_device.argtypes = [vp, C.c_int, vp, sz, sz, vp, sz, vp, vp, vp]
     lib.w3_pack_device.argtypes = [vp, C.c_int, vp, sz, vp, sz, vp, vp, vp]
     lib.w3_decode_device.argtypes = [vp, C.c_int, vp, vp, sz, sz, sz, vp, vp, vp]
@@ -223,6 +225,22 @@ class Context:
         out = C.create_string_buffer(max(n, 1))
         ol = C.c_size_t()
         check(self.lib.w3_decompress(self.handle, _addr(blob), len(blob), C.addressof(out), n, C.byref(ol)))
+        return out.raw[: ol.value]
+
+    # ---- the hashed context-mixing stack (include/w3_codec.h, w3_cm_*) ---------------------
+    def cm_compress(self, data: bytes, block_size: int = DEFAULT_BLOCK, log_cells: int = 16) -> bytes:
+        n = len(data)
+        cap = n + n // 4 + 4096 + 4 * (n // block_size + 1)
+        out = C.create_string_buffer(cap)
+        ol = C.c_size_t()
+        check(self.lib.w3_cm_compress(self.handle, _addr(data), n, block_size, log_cells, C.addressof(out), cap, C.byref(ol)))
+        return out.raw[: ol.value]
+
+    def cm_decompress(self, blob: bytes) -> bytes:
+        n = int.from_bytes(blob[8:16], "big") if len(blob) >= 16 else 0
+        out = C.create_string_buffer(max(n, 1))
+        ol = C.c_size_t()
+        check(self.lib.w3_cm_decompress(self.handle, _addr(blob), len(blob), C.addressof(out), n, C.byref(ol)))
         return out.raw[: ol.value]
 
     # ---- device-resident API (pointers are ints; stream is a cudaStream_t int)

@@ -49,6 +49,7 @@ static int cuda_fail(cudaError_t e, const char *what) {
     if (e_ != cudaSuccess) return cuda_fail(e_, #call);       \
   } while (0)
 
+#define W3_CM_MODELS_HOST 6 /* W3_CM_MODELS of w3_cm.cuh */
 static const uint8_t MAGIC_LEGACY[4] = {'w', '3', '0', 'i'}; /* src/main.rs:14 */
 static const uint8_t MAGIC_BLOCKS[4] = {'w', '3', 'B', 'k'};
 static const size_t HDR_LEGACY = 12, HDR_BLOCKS = 24, HDR_MODEL = 16; /* v2 appends the 8 u16 BE probabilities */
@@ -100,6 +101,7 @@ struct w3_dev {
   w3_hashtab *d_tab = nullptr;
   w3_buf in, scratch, scratch2, lens, lens2, alt, offsets, packed, out;
   w3_buf geo_H, geo_counters, geo_jobs; /* run-time geometry (w3_geo.cu) */
+  w3_buf cm_cells;                      /* hashed context mixing (w3_cm.cu) */
   uint32_t *d_flag = nullptr;
 };
 
@@ -133,6 +135,7 @@ static int dev_init(w3_dev &d, int ordinal) {
   d.sm_count = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
   CK(w3_kernels_init());
+  CK(w3_cm_init());
   CK(cudaMalloc(&d.d_tab, sizeof(w3_hashtab)));
   CK(cudaMalloc(&d.d_flag, sizeof(uint32_t)));
   return W3_OK;
@@ -172,7 +175,7 @@ static int ctx_set_model(w3_ctx *ctx, const uint16_t *table) {
 static void dev_release(w3_dev &d) {
   cudaSetDevice(d.ordinal);
   d.in.release(); d.scratch.release(); d.scratch2.release(); d.lens.release(); d.lens2.release();
-  d.alt.release(); d.offsets.release(); d.geo_H.release(); d.geo_counters.release(); d.geo_jobs.release();
+  d.alt.release(); d.offsets.release(); d.geo_H.release(); d.geo_counters.release(); d.geo_jobs.release(); d.cm_cells.release();
   d.packed.release(); d.out.release();
   if (d.d_tab) cudaFree(d.d_tab);
   if (d.d_flag) cudaFree(d.d_flag);
@@ -825,6 +828,158 @@ int w3_sweep(w3_ctx *ctx, const uint8_t *in, size_t n, const uint16_t *table, co
     at += cnt;
   }
   return W3_OK;
+}
+
+/* ---- the hashed context-mixing stack (w3_cm.cu; specification: oracle/w3_cm_oracle.c) -------- */
+
+static const uint8_t MAGIC_CM[4] = {'w', '3', 'C', 'm'};
+static const size_t HDR_CM = 24;
+
+/* blocks whose cell tables (96 << log_cells bytes each) are resident at once */
+static size_t cm_batch_blocks(int log_cells) {
+  return std::max<size_t>(1, std::min<size_t>(4096, ((size_t)32 << 30) / ((size_t)W3_CELL_BYTES << log_cells)));
+}
+
+int w3_cm_compress(w3_ctx *ctx, const uint8_t *in, size_t n, size_t block_size, int log_cells, uint8_t *out,
+                   size_t cap, size_t *out_len) {
+  if (!ctx || !out_len || (!in && n) || (!out && cap) || log_cells < 4 || log_cells > 24) return W3_E_ARG;
+  if (!block_size) block_size = W3_DEFAULT_BLOCK;
+  if (block_size & 3) return W3_E_ARG;
+  if (block_size > ((size_t)64 << 20)) return fail_msg(W3_E_TOOBIG, "block size %zu exceeds 64 MiB", block_size);
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  const size_t nb = (n + block_size - 1) / block_size;
+  if (nb > 0xFFFFFFFFull) return W3_E_ARG;
+  const size_t hdr = HDR_CM + 4 * nb;
+  enc_part parts[W3_MAX_DEVICES];
+  for (int g = 0; g < ctx->n; g++) block_range(nb, ctx->n, g, parts[g].b0, parts[g].b1);
+  int rc = for_each_device(ctx, [&](int g) {
+    enc_part &part = parts[g];
+    w3_dev &d = ctx->d[g];
+    const size_t nbg = part.b1 - part.b0;
+    part.lens.assign(nbg, 0);
+    part.total = 0;
+    if (!nbg) return (int)W3_OK;
+    CK(cudaSetDevice(d.ordinal));
+    const size_t off = part.b0 * block_size, bytes = std::min(n, part.b1 * block_size) - off;
+    const size_t nbat = std::min(cm_batch_blocks(log_cells), nbg);
+    size_t stride = round_up(block_size + (block_size >> 3) + 64, 16);
+    int r;
+    if ((r = d.in.ensure(round_up(bytes, 4) + 16)) != W3_OK) return r;
+    if ((r = d.cm_cells.ensure(nbat * ((size_t)W3_CELL_BYTES << log_cells))) != W3_OK) return r;
+    if ((r = d.scratch.ensure(stride * nbat)) != W3_OK) return r;
+    if ((r = d.lens.ensure(nbat * 4)) != W3_OK) return r;
+    if ((r = d.offsets.ensure((nbat + 1) * 8)) != W3_OK) return r;
+    if ((r = d.packed.ensure(bytes + (bytes >> 3) + 64 * (nbg + 1))) != W3_OK) return r;
+    CK(cudaMemcpyAsync(d.in.p, in + off, bytes, cudaMemcpyHostToDevice, d.stream));
+    uint64_t packed_at = 0;
+    for (size_t first = 0; first < nbg; first += nbat) {
+      const size_t cnt = std::min(nbat, nbg - first);
+      const size_t boff = first * block_size, blen = std::min(bytes, (first + cnt) * block_size) - boff;
+      for (int attempt = 0;; attempt++) {
+        CK(cudaMemsetAsync(d.cm_cells.p, 0, cnt * ((size_t)W3_CELL_BYTES << log_cells), d.stream));
+        CK(cudaMemsetAsync(d.d_flag, 0, 4, d.stream));
+        CK(w3_launch_cm_encode((const uint8_t *)d.in.p + boff, blen, (uint32_t)block_size, (uint32_t)cnt, (uint8_t *)d.scratch.p,
+                               stride, (uint32_t *)d.lens.p, d.d_flag, (uint8_t *)d.cm_cells.p, (uint32_t)log_cells, d.stream));
+        uint32_t flag = 0;
+        CK(cudaMemcpyAsync(&flag, d.d_flag, 4, cudaMemcpyDeviceToHost, d.stream));
+        CK(cudaMemcpyAsync(part.lens.data() + first, d.lens.p, cnt * 4, cudaMemcpyDeviceToHost, d.stream));
+        CK(cudaStreamSynchronize(d.stream));
+        if (!flag) break;
+        if (attempt) return fail_msg(W3_E_CUDA, "w3cm: a stream exceeded 12 bits per bit (flag %u)", flag);
+        /* the final probability stays within [1, 4095] / 4096: a coded bit costs at most 12 bits */
+        stride = round_up(12 * block_size + block_size / 2 + 64, 16);
+        if ((r = d.scratch.ensure(stride * nbat)) != W3_OK) return r;
+      }
+      uint64_t batch_total = 0;
+      for (size_t i = 0; i < cnt; i++) batch_total += part.lens[first + i];
+      if ((r = d.packed.grow_keep(packed_at + batch_total + 16, packed_at)) != W3_OK) return r;
+      CK(w3_launch_pack((const uint8_t *)d.scratch.p, stride, (const uint32_t *)d.lens.p, (uint32_t)cnt,
+                        (uint64_t *)d.offsets.p, nullptr, (uint8_t *)d.packed.p + packed_at, d.stream));
+      CK(cudaStreamSynchronize(d.stream));
+      packed_at += batch_total;
+    }
+    part.total = packed_at;
+    return (int)W3_OK;
+  });
+  if (rc != W3_OK) return rc;
+  uint64_t total = 0;
+  for (int g = 0; g < ctx->n; g++) total += parts[g].total;
+  *out_len = hdr + total;
+  if (*out_len > cap) return W3_E_CAP;
+  memcpy(out, MAGIC_CM, 4);
+  out[4] = 1; out[5] = (uint8_t)W3_CM_MODELS_HOST; out[6] = (uint8_t)log_cells; out[7] = 0;
+  put_be64(out + 8, (uint64_t)n);
+  put_be32(out + 16, (uint32_t)block_size);
+  put_be32(out + 20, (uint32_t)nb);
+  uint8_t *idx = out + HDR_CM;
+  for (int g = 0; g < ctx->n; g++)
+    for (uint32_t l : parts[g].lens) { put_be32(idx, l); idx += 4; }
+  uint64_t base[W3_MAX_DEVICES], run = hdr;
+  for (int g = 0; g < ctx->n; g++) { base[g] = run; run += parts[g].total; }
+  return for_each_device(ctx, [&](int g) {
+    w3_dev &d = ctx->d[g];
+    if (!parts[g].total) return (int)W3_OK;
+    CK(cudaSetDevice(d.ordinal));
+    CK(cudaMemcpyAsync(out + base[g], d.packed.p, parts[g].total, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    return (int)W3_OK;
+  });
+}
+
+int w3_cm_decompress(w3_ctx *ctx, const uint8_t *in, size_t n_in, uint8_t *out, size_t cap, size_t *out_len) {
+  if (!ctx || !in || !out_len || (!out && cap)) return W3_E_ARG;
+  if (n_in < 4 || memcmp(in, MAGIC_CM, 4)) return W3_E_MAGIC;
+  if (n_in < HDR_CM || in[4] != 1 || in[5] != W3_CM_MODELS_HOST || in[6] < 4 || in[6] > 24) return W3_E_FORMAT;
+  const int log_cells = in[6];
+  const size_t n = (size_t)get_be64(in + 8), bs = get_be32(in + 16), nb = get_be32(in + 20);
+  if (!bs || (bs & 3) || bs > ((size_t)64 << 20) || nb != (n + bs - 1) / bs) return W3_E_FORMAT;
+  const size_t hdr = HDR_CM + 4 * nb;
+  if (n_in < hdr) return W3_E_FORMAT;
+  std::vector<uint64_t> offs(nb + 1);
+  uint64_t run = 0;
+  for (size_t i = 0; i < nb; i++) {
+    const uint32_t len = get_be32(in + HDR_CM + 4 * i);
+    if (len > MAX_STREAM) return W3_E_FORMAT;
+    offs[i] = run;
+    run += len;
+  }
+  offs[nb] = run;
+  if (hdr + run != n_in) return W3_E_FORMAT;
+  *out_len = n;
+  if (n > cap) return W3_E_CAP;
+  if (!nb) return W3_OK;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  return for_each_device(ctx, [&](int g) {
+    size_t b0, b1;
+    block_range(nb, ctx->n, g, b0, b1);
+    if (b0 == b1) return (int)W3_OK;
+    w3_dev &d = ctx->d[g];
+    CK(cudaSetDevice(d.ordinal));
+    const size_t nbg = b1 - b0;
+    const uint64_t c0 = offs[b0], clen = offs[b1] - c0;
+    const size_t o0 = b0 * bs, obytes = std::min(n, b1 * bs) - o0;
+    const size_t nbat = std::min(cm_batch_blocks(log_cells), nbg);
+    int r;
+    if ((r = d.packed.ensure(clen + 16)) != W3_OK) return r;
+    if ((r = d.offsets.ensure((nbg + 1) * 8)) != W3_OK) return r;
+    if ((r = d.out.ensure(round_up(obytes, 4) + 16)) != W3_OK) return r;
+    if ((r = d.cm_cells.ensure(nbat * ((size_t)W3_CELL_BYTES << log_cells))) != W3_OK) return r;
+    std::vector<uint64_t> rel(nbg + 1);
+    for (size_t i = 0; i <= nbg; i++) rel[i] = offs[b0 + i] - c0;
+    CK(cudaMemsetAsync((uint8_t *)d.packed.p + clen, 0, 16, d.stream));
+    if (clen) CK(cudaMemcpyAsync(d.packed.p, in + hdr + c0, clen, cudaMemcpyHostToDevice, d.stream));
+    CK(cudaMemcpyAsync(d.offsets.p, rel.data(), (nbg + 1) * 8, cudaMemcpyHostToDevice, d.stream));
+    for (size_t first = 0; first < nbg; first += nbat) {
+      const size_t cnt = std::min(nbat, nbg - first);
+      const size_t boff = first * bs, blen = std::min(obytes, (first + cnt) * bs) - boff;
+      CK(cudaMemsetAsync(d.cm_cells.p, 0, cnt * ((size_t)W3_CELL_BYTES << log_cells), d.stream));
+      CK(w3_launch_cm_decode((const uint8_t *)d.packed.p, (const uint64_t *)d.offsets.p + first, blen, (uint32_t)bs, (uint32_t)cnt,
+                             (uint8_t *)d.out.p + boff, d.d_flag, (uint8_t *)d.cm_cells.p, (uint32_t)log_cells, d.stream));
+    }
+    CK(cudaMemcpyAsync(out + o0, d.out.p, obytes, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    return (int)W3_OK;
+  });
 }
 
 /* ---- self-tests ------------------------------------------------------------ */

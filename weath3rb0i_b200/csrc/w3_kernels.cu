@@ -750,13 +750,12 @@ cudaError_t w3_launch_decode(const uint8_t *d_comp, const uint64_t *d_offsets, u
   /* lanes: `resident` blocks per CTA at a time, spread over `warps` warps (one per SM
    * sub-partition by default) of `lanes` blocks each; the pair form (two lanes per block, the next
    * position's lookup overlapping the current bit's coder step) unless the lane form is asked for.
-   * While all of an SM's blocks fit with 16 KiB each, the pair form keeps Counter::p of every
-   * counter in a second table (the chain per bit is what a step costs then); beyond that,
-   * residency matters more and the probability is recomputed from the counts. */
+   * Form 3 keeps Counter::p of every counter in a second table (16 KiB per block). */
   const int form = opts ? opts->lane_form : 0;
   const uint32_t q = w3_ceil_div(n_blocks, (uint32_t)sm_count);
   const bool pair = form != 1;
-  const bool cache_p = pair && (form == 3 || (form == 0 && q <= w3_lane_cap() / 2u));
+  (void)q;
+  const bool cache_p = pair && form == 3; /* measured slower than recomputing (profiles/r02_pair_variants.txt): on request only */
   const uint32_t cap = cache_p ? w3_lane_cap() / 2u : w3_lane_cap();
   const uint32_t per = w3_per_cta(n_blocks, sm_count, cap);
   uint32_t warps = per < 4u ? per : 4u;

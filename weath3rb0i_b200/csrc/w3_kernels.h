@@ -48,6 +48,14 @@ cudaError_t w3_launch_ac_encode_probs(const uint8_t *d_in, const uint16_t *d_pro
                                       uint32_t *d_out_len, cudaStream_t s);
 cudaError_t w3_launch_ac_decode_probs(const uint8_t *d_in, uint32_t n_in, const uint16_t *d_probs,
                                       uint32_t n_probs, uint8_t *d_out, cudaStream_t s);
+/* the hashed context-mixing stack (w3_cm.cu): one warp per block, cells = n_blocks x (96 << log_cells) zeroed bytes */
+cudaError_t w3_cm_init(void);
+cudaError_t w3_launch_cm_encode(const uint8_t *d_in, uint64_t n_total, uint32_t block_size, uint32_t n_blocks,
+                                uint8_t *d_scratch, uint64_t stride, uint32_t *d_lens, uint32_t *d_err, uint8_t *d_cells,
+                                uint32_t log_cells, cudaStream_t s);
+cudaError_t w3_launch_cm_decode(const uint8_t *d_comp, const uint64_t *d_offsets, uint64_t n_total, uint32_t block_size,
+                                uint32_t n_blocks, uint8_t *d_out, uint32_t *d_err, uint8_t *d_cells, uint32_t log_cells,
+                                cudaStream_t s);
 /* Tier B (w3_tierb.cu): NaiveStateTable built on the device; the hash-slot unit self-test */
 cudaError_t w3_launch_build_state_table(struct w3_state_entry *d_table, struct w3_state_entry *d_aux, cudaStream_t s);
 cudaError_t w3_launch_hashslot_ops(const uint32_t *d_ops, uint32_t n_ops, uint8_t *d_cells, uint32_t *d_res, cudaStream_t s);

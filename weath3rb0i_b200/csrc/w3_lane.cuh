@@ -55,6 +55,16 @@
 #ifndef W3_LANE_FIX
 #define W3_LANE_FIX 4
 #endif
+#ifndef W3_PAIR_EARLY_REPAIR
+/* 1: repair a declined lookup where it is made (a branch inside B); 0: just before the pick, which
+ * keeps B and the next F in one basic block.  Measured on 1 GiB / 1024 blocks
+ * (profiles/r02_pair_variants.txt): early 1334 ms, late 1684 ms without the probability table;
+ * with it 1671 / 1436.  The early form without the table is the default. */
+#define W3_PAIR_EARLY_REPAIR 1
+#endif
+#ifndef W3_LANE_MINB
+#define W3_LANE_MINB 1 /* __launch_bounds__ minimum CTAs per SM of the lane kernels (register budget) */
+#endif
 #define W3_LANE_ROW 264u /* 255 thresholds + padding: a lookup reads W3_LANE_FIX entries from any base <= 255 */
 static_assert(255u + W3_LANE_FIX <= W3_LANE_ROW, "threshold rows must cover the read-ahead");
 
@@ -310,6 +320,13 @@ W3_HD w3_pair_cand w3_pair_guess(const w3_pair_dec &s, uint32_t g, uint32_t a2, 
   c.glo = w3_fsr(s.klo, s.khi, 1u);
   const uint32_t r = w3_lane_rank(c.gk, a2, m, c.bad);
   c.ci = (((r & 255u) << W3_ALIGN_BITS) | a2) * 4u; /* r <= 255 unless bad: the load below stays inside the table */
+#if W3_PAIR_EARLY_REPAIR
+  if (c.bad) {
+    const uint32_t rr = w3_lane_rank_slow(c.gk, c.glo, a2, m.g);
+    c.ci = ((rr << W3_ALIGN_BITS) | a2) * 4u;
+    c.bad = false;
+  }
+#endif
   c.P = w3_pair_P_of<kCacheP>(c.ci, m);             /* of a wrong counter if bad: repaired before the pick */
   return c;
 }
@@ -361,7 +378,7 @@ __device__ __forceinline__ w3_lane_mem w3_lane_mem_of(w3_lane_tab *lt, uint32_t 
   return m;
 }
 
-__global__ void __launch_bounds__(W3_LANE_MAX_WARPS * 32u, 1)
+__global__ void __launch_bounds__(W3_LANE_MAX_WARPS * 32u, W3_LANE_MINB)
 w3_decode_blocks_lane(const uint8_t *__restrict__ comp, const uint64_t *__restrict__ offsets, uint32_t n_blocks,
                       uint32_t block_size, uint64_t n_total, uint8_t *__restrict__ out, uint32_t *__restrict__ err,
                       const w3_hashtab *__restrict__ tab, uint32_t lanes) {
@@ -394,7 +411,7 @@ w3_decode_blocks_lane(const uint8_t *__restrict__ comp, const uint64_t *__restri
  * the warp (same values, same stores), a short last block keeps stepping over its exhausted
  * stream without storing. */
 template <bool kCacheP>
-__global__ void __launch_bounds__(W3_LANE_MAX_WARPS * 32u, 1)
+__global__ void __launch_bounds__(W3_LANE_MAX_WARPS * 32u, W3_LANE_MINB)
 w3_decode_blocks_pair(const uint8_t *__restrict__ comp, const uint64_t *__restrict__ offsets, uint32_t n_blocks,
                       uint32_t block_size, uint64_t n_total, uint8_t *__restrict__ out, uint32_t *__restrict__ err,
                       const w3_hashtab *__restrict__ tab, uint32_t pairs) {
@@ -436,9 +453,11 @@ w3_decode_blocks_pair(const uint8_t *__restrict__ comp, const uint64_t *__restri
     const uint32_t n_steps = block_size < n_total ? block_size : (uint32_t)n_total; /* the same for every lane */
     auto step = [&](auto careful, uint32_t a) -> uint32_t {
       const uint32_t bit = w3_pair_front<decltype(careful)::value, kCacheP>(s, m, ab, end_bits); /* F */
+#if !W3_PAIR_EARLY_REPAIR
       if (__any_sync(0xFFFFFFFFu, cand.bad)) {
         if (cand.bad) w3_pair_repair<kCacheP>(cand, (a + 1u) & 7u, m);
       }
+#endif
       const uint32_t src = (lane & 30u) | bit;                                                   /* pick */
       s.ci = __shfl_sync(0xFFFFFFFFu, cand.ci, src);
       s.P = __shfl_sync(0xFFFFFFFFu, cand.P, src);
