@@ -2,7 +2,7 @@
 (device-resident input, CUDA events) for a list of launch options and says whether the round trip
 matched and whether the packed streams equal those of the first configuration.  Never a bench number.
 
-usage: python scripts/exp_many.py MIB BLOCK_KIB "kernels:enc_teams:lane_warps[:lane_form]" ...
+usage: python scripts/exp_many.py MIB BLOCK_KIB "kernels:enc_teams:lane_warps[:lane_form[:enc_coder]]" ...
 """
 import hashlib
 import os
@@ -53,6 +53,7 @@ for cfg in configs:
     k, teams, warps, *rest = cfg.split(":")
     ctx.set_kernels(k)
     ctx.set_option(capi.W3_OPT_LANE_FORM, int(rest[0]) if rest else 0)
+    ctx.set_option(capi.W3_OPT_ENC_CODER, int(rest[1]) if len(rest) > 1 else 0)
     ctx.set_option(capi.W3_OPT_ENC_TEAMS, int(teams))
     ctx.set_option(capi.W3_OPT_LANE_WARPS, int(warps))
     d_flag.zero_()

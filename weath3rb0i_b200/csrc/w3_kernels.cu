@@ -666,7 +666,10 @@ cudaError_t w3_kernels_init(void) {
   e = cudaFuncSetAttribute(w3_decode_blocks_warp, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)w3_dense_dec_smem_bytes(W3_MAX_WARPS));
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(w3_encode_blocks_team, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = cudaFuncSetAttribute(w3_encode_blocks_team<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(sizeof(w3_smem_tab) + W3_ENC_TEAM_MAXB * sizeof(w3_enc_team)));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(w3_encode_blocks_team<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)(sizeof(w3_smem_tab) + W3_ENC_TEAM_MAXB * sizeof(w3_enc_team)));
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(w3_decode_blocks_team, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -701,9 +704,16 @@ cudaError_t w3_launch_encode(const uint8_t *d_in, uint64_t n_total, uint32_t blo
   uint32_t teams = 1u;
   if (k != W3_K_TEAM) teams = w3_per_cta(n_blocks, sm_count, W3_ENC_TEAM_MAXB);
   if (opts && opts->enc_teams > 0) teams = (uint32_t)opts->enc_teams < W3_ENC_TEAM_MAXB ? (uint32_t)opts->enc_teams : W3_ENC_TEAM_MAXB;
-  w3_encode_blocks_team<<<w3_ceil_div(n_blocks, teams), W3_ENC_TEAM_THREADS * teams,
-                          sizeof(w3_smem_tab) + teams * sizeof(w3_enc_team), s>>>(
-      d_in, n_total, block_size, n_blocks, d_scratch, stride, d_lens, d_overflow, d_tab);
+  /* from two teams per CTA on, one coder warp serves them all (lane b = team b) */
+  const bool lane_coder = teams >= 2u && !(opts && opts->enc_coder == 1);
+  if (lane_coder)
+    w3_encode_blocks_team<true><<<w3_ceil_div(n_blocks, teams), W3_ENC_LANE_THREADS(teams),
+                                  sizeof(w3_smem_tab) + teams * sizeof(w3_enc_team), s>>>(
+        d_in, n_total, block_size, n_blocks, d_scratch, stride, d_lens, d_overflow, d_tab, teams);
+  else
+    w3_encode_blocks_team<false><<<w3_ceil_div(n_blocks, teams), W3_ENC_TEAM_THREADS * teams,
+                                   sizeof(w3_smem_tab) + teams * sizeof(w3_enc_team), s>>>(
+        d_in, n_total, block_size, n_blocks, d_scratch, stride, d_lens, d_overflow, d_tab, teams);
   return cudaGetLastError();
 }
 

@@ -112,8 +112,10 @@ struct w3_enc_team {
   uint32_t wr_done;                   /* groups consumed by the writer warp */
   uint32_t final_x2;                  /* x2 at the end of the block, for ac.flush */
   uint32_t abort_flag;
-  uint32_t pad[2];
+  uint32_t pad[28];                   /* the size in words is 2 mod 32: lane b of the lane coder addresses team b,
+                                         and the eight teams' entries fall into different banks (8-byte accesses too) */
 };
+static_assert((sizeof(w3_enc_team) / 4u) % 32u == 2u && sizeof(w3_enc_team) % 8u == 0u, "team stride: bank spread of the lane coder");
 
 #define W3_ENC_TEAM_THREADS 96 /* per team: coder, model and writer warp */
 /* Teams per CTA.  One team per CTA leaves an SM at three resident blocks (the
@@ -123,26 +125,110 @@ struct w3_enc_team {
  * three leaves idle. */
 #define W3_ENC_TEAM_MAXB 8u
 
+/* kLaneCoder: ONE coder warp for all the CTA's teams, lane b coding block b — the coder's 22
+ * instructions per coded bit are then issued once per CTA instead of once per team (47 warp
+ * instructions per coded bit and team made seven teams per SM pipe-bound: 134 cycles per bit;
+ * the lone coder warp paces at ~60-70).  Warps: 0 the coder, 1..B the model warps, B+1..2B the
+ * writer warps.  The per-team rings and flags are unchanged; the coder warp waits until every
+ * active lane's group is there. */
+#define W3_ENC_LANE_THREADS(teams) (32u * (1u + 2u * (teams)))
+
+template <bool kLaneCoder>
 __global__ void __launch_bounds__(W3_ENC_TEAM_THREADS * W3_ENC_TEAM_MAXB, 1)
 w3_encode_blocks_team(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t block_size,
                       uint32_t n_blocks, uint8_t *__restrict__ scratch, uint64_t stride,
                       uint32_t *__restrict__ lens, uint32_t *__restrict__ err,
-                      const w3_hashtab *__restrict__ tab) {
+                      const w3_hashtab *__restrict__ tab, uint32_t n_teams) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   w3_smem_tab *st = reinterpret_cast<w3_smem_tab *>(smem_raw);
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t team = (threadIdx.x >> 5) / 3u, warp = (threadIdx.x >> 5) % 3u, n_teams = blockDim.x / W3_ENC_TEAM_THREADS;
-  w3_enc_team *tm = reinterpret_cast<w3_enc_team *>(smem_raw + sizeof(w3_smem_tab)) + team;
+  w3_enc_team *t0 = reinterpret_cast<w3_enc_team *>(smem_raw + sizeof(w3_smem_tab));
+  const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+  /* role: 0 coder, 1 model, 2 writer */
+  const uint32_t team = kLaneCoder ? (wid == 0u ? 0u : (wid - 1u) % n_teams) : wid / 3u;
+  const uint32_t warp = kLaneCoder ? (wid == 0u ? 0u : 1u + (wid - 1u) / n_teams) : wid % 3u;
+  w3_enc_team *tm = t0 + team;
 
   w3_load_tab(st, tab);
-  {
-    w3_enc_team *t0 = reinterpret_cast<w3_enc_team *>(smem_raw + sizeof(w3_smem_tab));
-    for (uint32_t i = threadIdx.x; i < n_teams * W3_NCTX; i += blockDim.x) t0[i / W3_NCTX].stats[i % W3_NCTX] = 0u;
-  }
-  if (warp == 0 && lane == 0) {
-    tm->prod_done = 0; tm->cons_done = 0; tm->out_done = 0; tm->wr_done = 0; tm->abort_flag = 0;
+  for (uint32_t i = threadIdx.x; i < n_teams * W3_NCTX; i += blockDim.x) t0[i / W3_NCTX].stats[i % W3_NCTX] = 0u;
+  if (threadIdx.x < n_teams) {
+    w3_enc_team *t = t0 + threadIdx.x;
+    t->prod_done = 0; t->cons_done = 0; t->out_done = 0; t->wr_done = 0; t->abort_flag = 0; t->final_x2 = 0xFFFFFFFFu;
   }
   __syncthreads();
+
+  /* one abort flag per CTA when the coder warp is shared: a wait that gives up must release everybody */
+  const uint32_t abort_a = w3_saddr(kLaneCoder ? &t0->abort_flag : &tm->abort_flag);
+
+  if (kLaneCoder && wid == 0u) {
+    /* ---- lane coder: lane b runs the coder of team b (see the coder warp below for the step) ---- */
+    const uint32_t blk_l = blockIdx.x * n_teams + lane;
+    const bool has = lane < n_teams && blk_l < n_blocks;
+    w3_enc_team *my = t0 + (has ? lane : 0u);
+    const uint64_t off_l = (uint64_t)blk_l * block_size;
+    const uint32_t n_l = has ? (uint32_t)(n_total - off_l < block_size ? n_total - off_l : block_size) : 0u;
+    const uint32_t words_l = (n_l + 3u) >> 2;
+    uint32_t max_words = words_l;
+#pragma unroll
+    for (uint32_t d = 16; d; d >>= 1) {
+      const uint32_t o = __shfl_xor_sync(FULL, max_words, d);
+      max_words = o > max_words ? o : max_words;
+    }
+    const uint32_t prod_l = w3_saddr(&my->prod_done), cons_l = w3_saddr(&my->cons_done);
+    const uint32_t out_l = w3_saddr(&my->out_done), wr_l = w3_saddr(&my->wr_done), fx2_l = w3_saddr(&my->final_x2);
+    const uint32_t ring_l = w3_saddr(&my->ring[0][0]), oring_l = w3_saddr(&my->oring[0][0]);
+    w3_coder cw = w3_coder_new();
+    const uint32_t ones = w3_lds(w3_saddr(&t0->final_x2)); /* 0xFFFFFFFF in a register ptxas cannot fold */
+    auto coder_step = [&](uint32_t vj) -> uint2 {
+      uint32_t flip, x1p, x2p;
+      (void)w3_coder_step<false>(cw, vj & 1u, vj & 0xFFFF0000u, flip, x1p, x2p, ones);
+      return make_uint2(x1p, x2p);
+    };
+    uint32_t ready = 0, room = W3_OUT_RING;
+    for (uint32_t g = 0; g < max_words; g++) {
+      const bool active = has && g < words_l;
+      if (__any_sync(FULL, active && ready <= g)) { /* every active lane's group g must be there */
+        uint32_t spins = 0;
+        for (;;) {
+          if (active) ready = w3_lds(prod_l);
+          if (__all_sync(FULL, !active || (int32_t)(ready - g) > 0)) break;
+          if (++spins > W3_SPIN_LIMIT || w3_lds(abort_a)) { w3_sts(abort_a, 1u); return; }
+        }
+      }
+      if (__any_sync(FULL, active && g >= room)) { /* and room in every active lane's output ring */
+        uint32_t spins = 0;
+        for (;;) {
+          if (active) room = w3_lds(wr_l) + W3_OUT_RING;
+          if (__all_sync(FULL, !active || g < room)) break;
+          if (++spins > W3_SPIN_LIMIT || w3_lds(abort_a)) { w3_sts(abort_a, 1u); return; }
+        }
+      }
+      const uint32_t ga = ring_l + (g & (W3_ENC_RING - 1u)) * 128u;
+      const uint32_t oa = oring_l + (g & (W3_OUT_RING - 1u)) * 256u;
+      const uint32_t left = n_l * 8u - g * 32u;
+      if (__all_sync(FULL, !active || left >= 32u)) {
+        uint32_t v0 = w3_lds(ga), v1 = w3_lds(ga + 4u);
+#pragma unroll
+        for (uint32_t j = 0; j < 32u; j++) {
+          const uint32_t vj = v0;
+          v0 = v1;
+          if (j + 2u < 32u) v1 = w3_lds(ga + (j + 2u) * 4u);
+          const uint2 r = coder_step(vj);
+          if (active) w3_sts64(oa + j * 8u, r);
+        }
+      } else {
+        for (uint32_t j = 0; j < 32u; j++) { /* a short last group: bounds that emit nothing past its end */
+          if (active) w3_sts64(oa + j * 8u, j < left ? coder_step(w3_lds(ga + j * 4u)) : make_uint2(0u, 0xFFFFFFFFu));
+        }
+      }
+      if (active) {
+        w3_sts(cons_l, g + 1u);
+        if (g + 1u == words_l) w3_sts(fx2_l, cw.x1 + cw.w);
+      }
+      __threadfence_block();
+      if (active) w3_sts(out_l, g + 1u);
+    }
+    return; /* an empty block never started its coder: final_x2 is still new_coder's (set above) */
+  }
 
   const uint32_t blk = blockIdx.x * n_teams + team;
   if (blk >= n_blocks) return;
@@ -152,7 +238,6 @@ w3_encode_blocks_team(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t
   const uint32_t ring_a = w3_saddr(&tm->ring[0][0]) + lane * 4u;
   const uint32_t prod_a = w3_saddr(&tm->prod_done), cons_a = w3_saddr(&tm->cons_done);
   const uint32_t out_a = w3_saddr(&tm->out_done), wr_a = w3_saddr(&tm->wr_done);
-  const uint32_t abort_a = w3_saddr(&tm->abort_flag);
 
   if (warp == 1) {
     /* ---- model warp: (bit, p) for 32 positions per pass -------------------- */
@@ -233,7 +318,7 @@ w3_encode_blocks_team(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t
     return;
   }
 
-  if (warp == 0) {
+  if (!kLaneCoder && warp == 0) {
     /* ---- coder warp: the range chain of ac.encode (main.rs:107) and nothing
      * else, carried as (x1, width) with one clz per step (w3_coder_step).  A
      * lone warp pays 2.3-2.7 cycles per INSTRUCTION, on or off the chain
