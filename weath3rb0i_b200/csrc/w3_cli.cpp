@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <string>
 #include <vector>
 
@@ -212,7 +213,11 @@ static int do_decompress(w3_ctx *ctx, const std::string &in, const std::string &
   size_t n = 0;
   int rc = w3_decompressed_size(blob.data(), blob.size(), &n);
   if (rc != W3_OK) return fail("decompress", rc);
-  std::vector<uint8_t> data(n ? n : 1);
+  /* the length comes from an untrusted header: a coded bit costs at least log2(65536/65535) bits
+   * (p <= 65535/65536), so a stream of s bytes cannot hold more than ~45427 * 8 * s bits */
+  if (n / 45427 > blob.size() + 64) { fprintf(stderr, "w3: %s: the header claims %zu bytes for a %zu-byte file\n", in.c_str(), n, blob.size()); return 1; }
+  std::vector<uint8_t> data;
+  try { data.resize(n ? n : 1); } catch (const std::exception &) { fprintf(stderr, "w3: %s: cannot allocate %zu bytes\n", in.c_str(), n); return 1; }
   rc = w3_decompress(ctx, blob.data(), blob.size(), data.data(), n, &n);
   if (rc != W3_OK) return fail("decompress", rc);
   if (!write_file(out, data.data(), n)) { perror(out.c_str()); return 1; }

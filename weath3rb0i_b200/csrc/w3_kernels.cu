@@ -704,8 +704,9 @@ cudaError_t w3_launch_encode(const uint8_t *d_in, uint64_t n_total, uint32_t blo
   uint32_t teams = 1u;
   if (k != W3_K_TEAM) teams = w3_per_cta(n_blocks, sm_count, W3_ENC_TEAM_MAXB);
   if (opts && opts->enc_teams > 0) teams = (uint32_t)opts->enc_teams < W3_ENC_TEAM_MAXB ? (uint32_t)opts->enc_teams : W3_ENC_TEAM_MAXB;
-  /* from two teams per CTA on, one coder warp serves them all (lane b = team b) */
-  const bool lane_coder = teams >= 2u && !(opts && opts->enc_coder == 1);
+  /* from three teams per CTA on, one coder warp serves them all (lane b = team b); measured on 1 GiB
+   * (profiles/r02_encode_lane_coder.txt): 7 teams 402 against 579 ms, 4 teams 369 / 372, 2 teams 347 / 323 */
+  const bool lane_coder = teams >= 3u && !(opts && opts->enc_coder == 1);
   if (lane_coder)
     w3_encode_blocks_team<true><<<w3_ceil_div(n_blocks, teams), W3_ENC_LANE_THREADS(teams),
                                   sizeof(w3_smem_tab) + teams * sizeof(w3_enc_team), s>>>(

@@ -128,10 +128,12 @@ static_assert((sizeof(w3_enc_team) / 4u) % 32u == 2u && sizeof(w3_enc_team) % 8u
 /* kLaneCoder: ONE coder warp for all the CTA's teams, lane b coding block b — the coder's 22
  * instructions per coded bit are then issued once per CTA instead of once per team (47 warp
  * instructions per coded bit and team made seven teams per SM pipe-bound: 134 cycles per bit;
- * the lone coder warp paces at ~60-70).  Warps: 0 the coder, 1..B the model warps, B+1..2B the
- * writer warps.  The per-team rings and flags are unchanged; the coder warp waits until every
+ * the lone coder warp paces at ~60-70).  Warp 0 is the coder; B model warps and B writer warps follow.  The per-team rings and flags are unchanged; the coder warp waits until every
  * active lane's group is there. */
-#define W3_ENC_LANE_THREADS(teams) (32u * (1u + 2u * (teams)))
+/* The coder warp has scheduler 0 to itself: worker k (model warps first, then writer warps) is warp
+ * k + 1 + k / 3, the other warps = 0 mod 4 exit at once (as in the team decoder). */
+#define W3_ENC_LANE_WARP_OF(k) ((k) + 1u + (k) / 3u)
+#define W3_ENC_LANE_THREADS(teams) (32u * (W3_ENC_LANE_WARP_OF(2u * (teams) - 1u) + 1u))
 
 template <bool kLaneCoder>
 __global__ void __launch_bounds__(W3_ENC_TEAM_THREADS * W3_ENC_TEAM_MAXB, 1)
@@ -143,9 +145,10 @@ w3_encode_blocks_team(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t
   w3_smem_tab *st = reinterpret_cast<w3_smem_tab *>(smem_raw);
   w3_enc_team *t0 = reinterpret_cast<w3_enc_team *>(smem_raw + sizeof(w3_smem_tab));
   const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-  /* role: 0 coder, 1 model, 2 writer */
-  const uint32_t team = kLaneCoder ? (wid == 0u ? 0u : (wid - 1u) % n_teams) : wid / 3u;
-  const uint32_t warp = kLaneCoder ? (wid == 0u ? 0u : 1u + (wid - 1u) / n_teams) : wid % 3u;
+  /* role: 0 coder, 1 model, 2 writer; lane coder: worker k = wid - 1 - wid / 4 for the warps that are not 0 mod 4 */
+  const uint32_t worker = wid - 1u - (wid >> 2);
+  const uint32_t team = kLaneCoder ? (wid == 0u ? 0u : worker % n_teams) : wid / 3u;
+  const uint32_t warp = kLaneCoder ? (wid == 0u ? 0u : 1u + worker / n_teams) : wid % 3u;
   w3_enc_team *tm = t0 + team;
 
   w3_load_tab(st, tab);
@@ -230,6 +233,7 @@ w3_encode_blocks_team(const uint8_t *__restrict__ in, uint64_t n_total, uint32_t
     return; /* an empty block never started its coder: final_x2 is still new_coder's (set above) */
   }
 
+  if (kLaneCoder && ((wid & 3u) == 0u || worker >= 2u * n_teams)) return; /* scheduler 0 belongs to the coder */
   const uint32_t blk = blockIdx.x * n_teams + team;
   if (blk >= n_blocks) return;
   const uint64_t off = (uint64_t)blk * block_size;
