@@ -306,7 +306,7 @@ def run_b200(args):
     h_comp = torch.empty(cap, dtype=torch.uint8).pin_memory()
     h_back = torch.empty(max(n, 1), dtype=torch.uint8).pin_memory()
     comp_np = h_comp.numpy()
-    per = (nb_total + world - 1) // world  # padded index slice per rank
+    per = sharding.lens_per_rank(nb_total, world)  # padded index slice per rank
     d_mylens = torch.zeros(per, dtype=torch.int32, device="cuda")
     d_alllens = torch.zeros(per * world, dtype=torch.int32, device="cuda")
     state = {"total": 0}
@@ -320,20 +320,15 @@ def run_b200(args):
             d_mylens.zero_()
             d_mylens[:nb].copy_(torch.from_numpy(lens.astype(np.int32)))
             dist.all_gather_into_tensor(d_alllens, d_mylens)
-            al = d_alllens.cpu().numpy().astype(np.int64).reshape(world, per)
-            all_lens = np.concatenate([al[r, : sharding.block_range(nb_total, world, r)[1] - sharding.block_range(nb_total, world, r)[0]]
-                                       for r in range(world)])
+            all_lens = np.asarray(sharding.flatten_gathered_lens(d_alllens.cpu().numpy().reshape(world, per), nb_total), dtype=np.int64)
         else:
             all_lens = lens
-        offs = np.concatenate([[0], np.cumsum(all_lens)])
-        mine = slice(hdr_total + int(offs[b0]), hdr_total + int(offs[b1]))
-        shm[mine] = comp_np[sharding.HDR_BLOCKS + 4 * nb: clen]  # this rank's streams, at their place
+        start, end, total = sharding.placement(n_total, block, world, rank, all_lens)
+        shm[start:end] = comp_np[sharding.HDR_BLOCKS + 4 * nb: clen]  # this rank's streams, at their place
         if rank == 0:
-            head = (sharding.MAGIC_BLOCKS + bytes([1, 0, 0, 0]) + n_total.to_bytes(8, "big") + block.to_bytes(4, "big")
-                    + nb_total.to_bytes(4, "big"))
-            shm[: sharding.HDR_BLOCKS] = np.frombuffer(head, dtype=np.uint8)
+            shm[: sharding.HDR_BLOCKS] = np.frombuffer(sharding.header_bytes(n_total, block, nb_total), dtype=np.uint8)
             shm[sharding.HDR_BLOCKS: hdr_total] = all_lens.astype(">u4").view(np.uint8)
-        state["total"] = hdr_total + int(offs[nb_total])
+        state["total"] = total
         barrier()  # the container is complete
         tb = time.perf_counter()
         if n:

@@ -39,6 +39,53 @@ def _rank_main(rank, world, port, n, block, out_path):
     dist.destroy_process_group()
 
 
+def _rank_in_place(rank, world, port, n, block, out_path):
+    """bench.py's e2e join: exchange only the stream lengths, every rank writes its streams at the
+    offsets the index implies into ONE shared file, rank 0 adds header and index."""
+    import numpy as np
+    import torch
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tests._libs import Oracle
+
+    oracle = Oracle()
+    nb = sharding.n_blocks_of(n, block)
+    lo, hi = sharding.byte_range(n, block, world, rank)
+    data = w3_corpus.generate(hi - lo, offset=lo)
+    streams = [oracle.compress_block(data[i : i + block]) for i in range(0, len(data), block)]
+    per = sharding.lens_per_rank(nb, world)
+    mine = torch.zeros(per, dtype=torch.int32)
+    mine[: len(streams)] = torch.tensor([len(s) for s in streams], dtype=torch.int32)
+    gathered = [torch.zeros(per, dtype=torch.int32) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    all_lens = sharding.flatten_gathered_lens([g.tolist() for g in gathered], nb)
+    start, end, total = sharding.placement(n, block, world, rank, all_lens)
+    if rank == 0:
+        with open(out_path, "wb") as f:
+            f.truncate(total)
+    dist.barrier()
+    shm = np.memmap(out_path, dtype=np.uint8, mode="r+", shape=(total,))
+    body = b"".join(streams)
+    assert end - start == len(body)
+    shm[start:end] = np.frombuffer(body, dtype=np.uint8)
+    if rank == 0:
+        head = sharding.header_bytes(n, block, nb) + sharding.index_bytes(all_lens)
+        shm[: len(head)] = np.frombuffer(head, dtype=np.uint8)
+    shm.flush()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,block", [(65536 * 5 + 777, 65536), (4096 * 7 + 1, 4096)])
+def test_two_ranks_join_in_place(tmp_path, libs, n, block):
+    out = str(tmp_path / "shared.w3bk")
+    mp.spawn(_rank_in_place, args=(2, _free_port(), n, block, out), nprocs=2, join=True)
+    data = w3_corpus.generate(n)
+    single = sharding.build_container(n, block, [libs.oracle.compress_block(data[i : i + block]) for i in range(0, n, block)])
+    assert open(out, "rb").read() == single
+
+
 @pytest.mark.parametrize("n,block", [(65536 * 5 + 777, 65536), (4096 * 3, 4096), (1000, 4096)])
 def test_two_ranks_equal_one(tmp_path, libs, n, block):
     out = str(tmp_path / "joined.bin")

@@ -92,3 +92,45 @@ def offsets_of(streams: Sequence[bytes]) -> List[int]:
         run += len(s)
         out.append(run)
     return out
+
+
+# ---- joining the ranks' streams in place (bench.py's e2e leg; tests/test_sharding_gloo.py) --------
+# The only thing the ranks of a multi-process job exchange is the per-block stream length (the
+# offset index, 4 bytes per block): from it every rank knows where its streams go in the ONE
+# container, and writes them there itself (a shared mapping, or pwrite into a shared file).
+
+
+def lens_per_rank(n_blocks: int, world: int) -> int:
+    """Slots per rank of the padded length array that an all_gather exchanges."""
+    return (n_blocks + world - 1) // world
+
+
+def flatten_gathered_lens(gathered: Sequence[Sequence[int]], n_blocks: int) -> List[int]:
+    """gathered[r][:] = rank r's padded lengths -> the index of the whole container."""
+    world = len(gathered)
+    out: List[int] = []
+    for r in range(world):
+        b0, b1 = block_range(n_blocks, world, r)
+        out += [int(v) for v in gathered[r][: b1 - b0]]
+    return out
+
+
+def header_bytes(n: int, block_size: int, n_blocks: int) -> bytes:
+    return MAGIC_BLOCKS + bytes([1, 0, 0, 0]) + n.to_bytes(8, "big") + block_size.to_bytes(4, "big") + n_blocks.to_bytes(4, "big")
+
+
+def index_bytes(all_lens: Sequence[int]) -> bytes:
+    return b"".join(int(v).to_bytes(4, "big") for v in all_lens)
+
+
+def placement(n: int, block_size: int, world: int, rank: int, all_lens: Sequence[int]) -> Tuple[int, int, int]:
+    """-> (byte offset of this rank's first stream in the container, one past its last, container length)."""
+    nb = n_blocks_of(n, block_size)
+    if len(all_lens) != nb:
+        raise ValueError("index length does not match n / block_size")
+    offs = [0]
+    for v in all_lens:
+        offs.append(offs[-1] + int(v))
+    hdr = HDR_BLOCKS + 4 * nb
+    b0, b1 = block_range(nb, world, rank)
+    return hdr + offs[b0], hdr + offs[b1], hdr + offs[nb]
