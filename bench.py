@@ -370,9 +370,8 @@ def run_b200(args):
         enc_ms, dec_ms = t_enc / K, t_dec / K
         decode_dom = dec_ms >= enc_ms
         dom_ms = max(enc_ms, dec_ms)
-        q = (nb + 147) // 148
-        if decode_dom:
-            dom = "w3_decode_blocks_team" if nb <= 148 else ("w3_decode_blocks_pair" if q <= 12 else "w3_decode_blocks_lane")
+        if decode_dom:  # the launcher's choice (w3_launch_decode): teams up to two waves of one CTA per SM, lanes beyond
+            dom = "w3_decode_blocks_team" if nb <= 2 * 148 else "w3_decode_blocks_pair"
         else:
             dom = "w3_encode_blocks_team"
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965
