@@ -109,8 +109,15 @@ int w3_ctx_get_geometry(const w3_ctx *ctx, int *bits_in_context, int *alignment_
 typedef struct w3_sweep_point {
   uint8_t ctx_bits, alignment_bits;
 } w3_sweep_point;
-int w3_sweep(w3_ctx *ctx, const uint8_t *in, size_t n, const uint16_t table[8], const w3_sweep_point *points,
-             size_t n_points, uint64_t *bit_counts, uint16_t table_used[8]);
+/* history: which History feeds the context —
+ *   W3_HISTORY_AC   ACHistory, the entropy hash (src/history/ac_history.rs): the `entropy-hashing-ac` binary
+ *                   (and `entropy-hashing-ac-cached`, whose ACHistoryCached memoises the same hash)
+ *   W3_HISTORY_RAW  the raw bits (RawHistory src/history/raw_history.rs = OrderN src/models/ordern.rs:36-45):
+ *                   the `ordern` binary (src/bin/ordern/main.rs:16-33, 66-81); table is ignored */
+#define W3_HISTORY_AC 0
+#define W3_HISTORY_RAW 1
+int w3_sweep(w3_ctx *ctx, int history, const uint8_t *in, size_t n, const uint16_t table[8],
+             const w3_sweep_point *points, size_t n_points, uint64_t *bit_counts, uint16_t table_used[8]);
 
 /* ---- the hashed context-mixing stack "w3cm" ----------------------------------
  * What BASELINE.json's north star describes and the reference only plans (README.md:6-10):

@@ -355,6 +355,13 @@ static inline void model_update(model *m, unsigned bit) {
 }
 
 /* ------------------------------------------------------------------------ */
+/* OrderN (raw bit history) — src/models/ordern.rs:4-46; compress() of the     */
+/* ordern sweep binary — src/bin/ordern/main.rs:66-81                          */
+
+/* bits ACStats counts for OrderN::new(ctx_bits, alignment_bits) over buf (csize printed = / 8) */
+int w3o_sweep_exec_ordern(const uint8_t *buf, size_t n, int ctx_bits, int alignment_bits, uint64_t *bit_count);
+
+/* ------------------------------------------------------------------------ */
 /* compress / decompress — src/main.rs:89-144                               */
 
 int w3o_compress_block(const uint8_t *in, size_t n, uint8_t *out, size_t cap,
@@ -470,6 +477,35 @@ static inline void ac_encode_stats(coder *c, unsigned bit, uint16_t prob, acstat
     c->x1 = (c->x1 << 1) & RLO_MOD;
     c->x2 = (c->x2 << 1) | RHI_MOD;
   }
+}
+
+int w3o_sweep_exec_ordern(const uint8_t *buf, size_t n, int ctx_bits, int alignment_bits, uint64_t *bit_count) {
+  if ((!buf && n) || !bit_count || ctx_bits < 1 || ctx_bits > 30 || alignment_bits < 0 || alignment_bits > 7 ||
+      alignment_bits > ctx_bits)
+    return W3O_E_ARG;
+  uint16_t(*stats)[2] = (uint16_t(*)[2])calloc((size_t)1 << ctx_bits, sizeof(uint16_t[2])); /* ordern.rs:16 */
+  if (!stats) return W3O_E_ARG;
+  uint32_t ctx = 0, history = 0;
+  uint8_t alignment = 0;
+  const uint32_t mask_bits = (uint32_t)(ctx_bits - alignment_bits);
+  const uint32_t mask = (uint32_t)(((uint64_t)1 << mask_bits) - 1);
+  const uint8_t alignment_mask = (uint8_t)((1u << alignment_bits) - 1);
+  coder ac;
+  coder_init(&ac);
+  acstats w = {0, 0};
+  for (size_t i = 0; i < n; i++)
+    for (int k = 7; k >= 0; k--) {
+      unsigned bit = (buf[i] >> k) & 1;
+      uint16_t p = w3o_counter_p(stats[ctx][0], stats[ctx][1]); /* predict — ordern.rs:28-30 */
+      w3o_counter_update(stats[ctx], (int)bit);                  /* adapt — :32-34 */
+      history = ((history << 1) | bit) & mask;                   /* update — :36-45 */
+      alignment = (uint8_t)((alignment + 1) & alignment_mask);
+      ctx = (history << alignment_bits) | alignment;
+      ac_encode_stats(&ac, bit, p, &w);
+    }
+  free(stats);
+  *bit_count = w.bit_count;
+  return W3O_OK;
 }
 
 /* exec(buf, ctx_bits, alignment_bits, ACHistory::new(ctx_bits - alignment_bits, model)) of the

@@ -114,6 +114,9 @@ int w3o_decompress_block_geo(const uint8_t *in, size_t n_in, const uint16_t *tab
  * ACStats sink (src/helpers.rs:60-90): *bit_count = bits counted; the printed csize is that / 8 */
 int w3o_sweep_exec(const uint8_t *buf, size_t n, const uint16_t *table, int ctx_bits, int alignment_bits,
                    uint64_t *bit_count);
+/* compress() of the ordern sweep binary (src/bin/ordern/main.rs:66-81): OrderN::new(ctx_bits,
+ * alignment_bits) — the raw bit history as context (src/models/ordern.rs:4-46) — into ACStats */
+int w3o_sweep_exec_ordern(const uint8_t *buf, size_t n, int ctx_bits, int alignment_bits, uint64_t *bit_count);
 /* StationaryModel::new(buf) — src/models/ac_hash/stationary.rs:14-34: the 8
  * bit-position probabilities of a buffer (index 0 = a byte's MSB) */
 void w3o_stationary_new(const uint8_t *buf, size_t n, uint16_t table[8]);

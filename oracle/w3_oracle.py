@@ -264,6 +264,25 @@ def sweep_exec(buf: bytes, ctx_bits: int, alignment_bits: int, table=BOOK1) -> i
     return sink.bit_count
 
 
+def sweep_exec_ordern(buf: bytes, ctx_bits: int, alignment_bits: int) -> int:
+    """compress() of the ordern sweep binary (src/bin/ordern/main.rs:66-81) with OrderN
+    (src/models/ordern.rs:4-46): bits counted by ACStats."""
+    stats = [[0, 0] for _ in range(1 << ctx_bits)]
+    ctx = history = alignment = 0
+    mask = (1 << (ctx_bits - alignment_bits)) - 1
+    sink, coder = StatsSink(), Coder()
+    for byte in buf:
+        for k in range(7, -1, -1):
+            bit = (byte >> k) & 1
+            p = counter_p(*stats[ctx])
+            counter_update(stats[ctx], bit)
+            history = ((history << 1) | bit) & mask
+            alignment = (alignment + 1) & ((1 << alignment_bits) - 1)
+            ctx = (history << alignment_bits) | alignment
+            coder.encode(bit, p, sink)
+    return sink.bit_count
+
+
 def compress_block(data: bytes, table=BOOK1, geo=(11, 3, 8)) -> bytes:
     """Stream after the 12-byte header — src/main.rs:99-111; geo = (bits_in_context,
     alignment_bits, max_bits) of OrderNEntropy::new / ACHistory::new (init_model: 11, 3, 8)."""

@@ -77,6 +77,7 @@ def load_oracle():
     o.w3o_compress_block_geo.argtypes = [u8p, sz, u16p, C.c_int, C.c_int, C.c_int, C.c_void_p, sz, C.POINTER(sz)]
     o.w3o_decompress_block_geo.argtypes = [u8p, sz, u16p, C.c_int, C.c_int, C.c_int, C.c_void_p, sz]
     o.w3o_sweep_exec.argtypes = [u8p, sz, u16p, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+    o.w3o_sweep_exec_ordern.argtypes = [u8p, sz, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
     o.w3o_compress_file.argtypes = [u8p, sz, C.c_void_p, sz, C.POINTER(sz)]
     o.w3o_decompress_file.argtypes = [u8p, sz, C.c_void_p, sz, C.POINTER(sz)]
     o.w3o_ctx_trace.argtypes = [u8p, sz, u16p]
@@ -172,6 +173,13 @@ class Oracle:
         rc = self.lib.w3o_cm_decompress_block(stream, len(stream), log_cells, out, n_out)
         assert rc == 0, rc
         return out.raw[:n_out]
+
+    def sweep_exec_ordern(self, data: bytes, ctx_bits: int, align_bits: int) -> int:
+        """bits ACStats counts for one point of the ordern sweep (raw-history OrderN)"""
+        bc = C.c_uint64()
+        rc = self.lib.w3o_sweep_exec_ordern(data, len(data), ctx_bits, align_bits, C.byref(bc))
+        assert rc == 0, rc
+        return bc.value
 
     def stationary_new(self, data: bytes):
         t = (C.c_uint16 * 8)()

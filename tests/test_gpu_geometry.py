@@ -89,6 +89,19 @@ def test_sweep_equals_oracle(ctx, libs):
     assert bits2[0] == libs.oracle.sweep_exec(data, 11, 3, None)
 
 
+def test_ordern_sweep_equals_oracle(ctx, libs):
+    """The `ordern` binary's grid (src/bin/ordern/main.rs:16-33): raw bit history as context."""
+    data = w3_corpus.generate(9000, offset=41)
+    points = [(c, a) for c in range(8, 18) for a in range(0, 5)] + [(24, 3), (30, 0)]
+    bits, _ = ctx.sweep(data, points, history="raw")
+    for (c, a), got in zip(points, bits):
+        assert got == libs.oracle.sweep_exec_ordern(data, c, a), (c, a)
+    path = os.environ.get("W3_BOOK1")
+    if path and os.path.exists(path):  # src/bin/ordern/book1.log:4,22
+        b, _ = ctx.sweep(open(path, "rb").read(), [(8, 3), (11, 3)], history="raw")
+        assert [v // 8 for v in b] == [444793, 388051]
+
+
 def test_sweep_larger_input_sampled_points(ctx, libs):
     data = w3_corpus.generate(1 << 18, offset=5)
     points = [(c, a) for c in range(8, 23) for a in range(0, 5)]

@@ -63,7 +63,7 @@ def load():
     lib.w3_train_model.argtypes = [vp, u8p, sz, vp]
     lib.w3_ctx_set_geometry.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     lib.w3_ctx_get_geometry.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
-    lib.w3_sweep.argtypes = [vp, u8p, sz, vp, vp, sz, vp, vp]
+    lib.w3_sweep.argtypes = [vp, C.c_int, u8p, sz, vp, vp, sz, vp, vp]
     lib.w3_compress_bound.argtypes = [sz, sz]
     lib.w3_compress_bound.restype = sz
     lib.w3_compress.argtypes = [vp, u8p, sz, sz, C.c_uint32, u8p, sz, C.POINTER(sz)]
@@ -163,15 +163,16 @@ class Context:
         check(self.lib.w3_ctx_get_geometry(self.handle, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
-    def sweep(self, data, points, table=None):
-        """exec() of src/bin/entropy-hashing-ac/main.rs:48-75 for every (ctx_bits, alignment_bits) of
+    def sweep(self, data, points, table=None, history="ac"):
+        """exec() of src/bin/entropy-hashing-ac/main.rs:48-75 (history="ac") or compress() of
+        src/bin/ordern/main.rs:66-81 (history="raw") for every (ctx_bits, alignment_bits) of
         `points`, all at once on the GPU: -> (bit counts, the StationaryModel table used)."""
         n = len(points)
         pts = (C.c_uint8 * (2 * n))(*[v for p in points for v in p])
         t = (C.c_uint16 * 8)(*table) if table is not None else None
         used = (C.c_uint16 * 8)()
         out = (C.c_uint64 * n)()
-        check(self.lib.w3_sweep(self.handle, _addr(data), len(data), C.addressof(t) if t is not None else None,
+        check(self.lib.w3_sweep(self.handle, {"ac": 0, "raw": 1}[history], _addr(data), len(data), C.addressof(t) if t is not None else None,
                                 C.addressof(pts), n, C.addressof(out), C.addressof(used)))
         return list(out), tuple(used)
 

@@ -470,7 +470,7 @@ static int encode_part_geo(w3_ctx *ctx, int g, const uint8_t *in, size_t n, size
     const size_t cnt = std::min(nbat, nb - first);
     const size_t boff = first * bs, blen = std::min(bytes, (first + cnt) * bs) - boff;
     for (int attempt = 0;; attempt++) {
-      CK(w3_launch_geo_hash((const uint8_t *)d.in.p + boff, blen, (uint32_t)bs, d_table, (uint32_t)ctx->max_bits,
+      CK(w3_launch_geo_hash((const uint8_t *)d.in.p + boff, blen, (uint32_t)bs, d_table, (uint32_t)ctx->max_bits, 0u,
                             (uint32_t *)d.geo_H.p, d.sm_count, d.stream));
       CK(cudaMemsetAsync(d.geo_counters.p, 0, cnt * ((size_t)4 << ctx->ctx_bits), d.stream));
       for (size_t i = 0; i < cnt; i++) {
@@ -760,9 +760,10 @@ int w3_ctx_get_geometry(const w3_ctx *ctx, int *bits_in_context, int *alignment_
 }
 
 /* the sweep of src/bin/entropy-hashing-ac/main.rs:20-37: every point is exec() (:48-75) into ACStats */
-int w3_sweep(w3_ctx *ctx, const uint8_t *in, size_t n, const uint16_t *table, const w3_sweep_point *points,
+int w3_sweep(w3_ctx *ctx, int history, const uint8_t *in, size_t n, const uint16_t *table, const w3_sweep_point *points,
              size_t n_points, uint64_t *bit_counts, uint16_t *table_used) {
   if (!ctx || (!in && n) || !points || !bit_counts || !n_points || n_points > 4096 || n > ((size_t)1 << 28)) return W3_E_ARG;
+  if (history != W3_HISTORY_AC && history != W3_HISTORY_RAW) return W3_E_ARG;
   int hmax = 0;
   for (size_t i = 0; i < n_points; i++) {
     const int mb = (int)points[i].ctx_bits - (int)points[i].alignment_bits; /* ACHistory::new(ctx_bits - alignment_bits, ..) — :24 */
@@ -787,7 +788,7 @@ int w3_sweep(w3_ctx *ctx, const uint8_t *in, size_t n, const uint16_t *table, co
   if (table_used) CK(cudaMemcpyAsync(table_used, d_table, 16, cudaMemcpyDeviceToHost, d.stream));
   /* one hash pass at the largest max_bits: a shorter hash is a prefix of a longer one */
   CK(w3_launch_geo_hash((const uint8_t *)d.in.p, n, (uint32_t)std::max<size_t>(round_up(n, 4), 4), d_table, (uint32_t)hmax,
-                        (uint32_t *)d.geo_H.p, d.sm_count, d.stream));
+                        history == W3_HISTORY_RAW ? 1u : 0u, (uint32_t *)d.geo_H.p, d.sm_count, d.stream));
   /* points in batches whose counter tables fit the device's free memory */
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));

@@ -49,8 +49,10 @@ __device__ __forceinline__ uint32_t w3_geo_ctx(uint32_t h, uint32_t t, uint32_t 
 
 /* H[first_bit + t] = ACHistory::hash after t bits of the block that bit belongs to; blocks of
  * block_size bytes restart the history (block_size a multiple of 4) */
+/* raw = 1: H = the last 32 bits themselves — RawHistory::hash (src/history/raw_history.rs:18-20), the
+ * context of OrderN (src/models/ordern.rs:36-45), for the `ordern` sweep binary */
 __global__ void w3_k_geo_hash(const uint8_t *__restrict__ in, uint64_t n, uint32_t block_size,
-                              const uint16_t *__restrict__ table, uint32_t max_bits, uint32_t *__restrict__ H) {
+                              const uint16_t *__restrict__ table, uint32_t max_bits, uint32_t raw, uint32_t *__restrict__ H) {
   __shared__ uint16_t tab[8];
   if (threadIdx.x < 8) tab[threadIdx.x] = table[threadIdx.x];
   __syncthreads();
@@ -74,7 +76,7 @@ __global__ void w3_k_geo_hash(const uint8_t *__restrict__ in, uint64_t n, uint32
     if (bitpos >= n * 8u) continue;
     const uint32_t hist_hi = __funnelshift_l(w1, w0, lane), hist_lo = __funnelshift_l(w2, w1, lane);
     const uint64_t bits = ((uint64_t)hist_hi << 32) | hist_lo; /* ACHistory.bits: newest bit lowest */
-    H[bitpos] = t == 0u ? 0u : w3_achash_exact(bits, t, tab, (int)max_bits).hash;
+    H[bitpos] = t == 0u ? 0u : raw ? hist_lo : w3_achash_exact(bits, t, tab, (int)max_bits).hash;
   }
 }
 
@@ -188,9 +190,9 @@ __global__ void w3_k_geo_decode(w3_geo_job *__restrict__ jobs, uint32_t n_jobs, 
 
 extern "C" {
 cudaError_t w3_launch_geo_hash(const uint8_t *d_in, uint64_t n, uint32_t block_size, const uint16_t *d_table,
-                               uint32_t max_bits, uint32_t *d_H, int sm_count, cudaStream_t s) {
+                               uint32_t max_bits, uint32_t raw, uint32_t *d_H, int sm_count, cudaStream_t s) {
   if (!n) return cudaSuccess;
-  w3_k_geo_hash<<<sm_count * 16, 256, 0, s>>>(d_in, n, block_size, d_table, max_bits, d_H);
+  w3_k_geo_hash<<<sm_count * 16, 256, 0, s>>>(d_in, n, block_size, d_table, max_bits, raw, d_H);
   return cudaGetLastError();
 }
 cudaError_t w3_launch_geo_encode(w3_geo_job *d_jobs, uint32_t n_jobs, uint32_t lanes, cudaStream_t s) {

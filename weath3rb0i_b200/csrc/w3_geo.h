@@ -22,7 +22,7 @@ struct w3_geo_job {
 extern "C" {
 #endif
 cudaError_t w3_launch_geo_hash(const uint8_t *d_in, uint64_t n, uint32_t block_size, const uint16_t *d_table,
-                               uint32_t max_bits, uint32_t *d_H, int sm_count, cudaStream_t s);
+                               uint32_t max_bits, uint32_t raw, uint32_t *d_H, int sm_count, cudaStream_t s);
 cudaError_t w3_launch_geo_encode(struct w3_geo_job *d_jobs, uint32_t n_jobs, uint32_t lanes, cudaStream_t s);
 cudaError_t w3_launch_geo_decode(struct w3_geo_job *d_jobs, uint32_t n_jobs, uint32_t lanes, const uint16_t *d_table,
                                  uint32_t max_bits, cudaStream_t s);

@@ -10,12 +10,13 @@ import time
 from . import capi
 
 
-def run(path: str, ctx_range=range(8, 31), align_range=range(0, 5), out=sys.stdout) -> dict:
+def run(path: str, ctx_range=range(8, 31), align_range=range(0, 5), out=sys.stdout, history="ac") -> dict:
     data = open(path, "rb").read()
     ctx = capi.Context([0])
     points = [(c, a) for c in ctx_range for a in align_range if a <= c]
     t0 = time.perf_counter()
-    bits, table = ctx.sweep(data, points)
+    bits, table = ctx.sweep(data, points, history=history)
+    tag = "eh-ac" if history == "ac" else "ordern"
     dt = time.perf_counter() - t0
     ctx.close()
     res = {p: b // 8 for p, b in zip(points, bits)}  # ACStats::result — helpers.rs:71-73
@@ -26,7 +27,7 @@ def run(path: str, ctx_range=range(8, 31), align_range=range(0, 5), out=sys.stdo
             if (c, a) not in res:
                 continue
             size = res[(c, a)]
-            print(f"[eh-ac] [ctx: {c:2}, align: {a}] csize: {size} (ratio {size / max(len(data), 1):.3f})", file=out)
+            print(f"[{tag}] [ctx: {c:2}, align: {a}] csize: {size} (ratio {size / max(len(data), 1):.3f})", file=out)
             if size <= best:  # `if res > best { continue }` — main.rs:27-32
                 best, arg = size, (c, a)
             if size <= best_all:
@@ -38,6 +39,6 @@ def run(path: str, ctx_range=range(8, 31), align_range=range(0, 5), out=sys.stdo
 
 
 if __name__ == "__main__":
-    if len(sys.argv) != 2:
-        raise SystemExit("usage: python -m weath3rb0i_b200.sweep FILE")
-    run(sys.argv[1])
+    if len(sys.argv) not in (2, 3) or (len(sys.argv) == 3 and sys.argv[1] not in ("eh-ac", "ordern")):
+        raise SystemExit("usage: python -m weath3rb0i_b200.sweep [eh-ac|ordern] FILE   (the reference's src/bin/<name>)")
+    run(sys.argv[-1], history="raw" if sys.argv[1] == "ordern" else "ac")
