@@ -89,3 +89,17 @@ def test_windowed_training_is_refused(w3, tmp_path):
     (tmp_path / "x.dat").write_bytes(w3_corpus.generate(200000, offset=5))
     p = run(w3, tmp_path, "-b", "65536", "-m", "train", "-w", "65536", "c", "x.dat", ok=False)
     assert p.returncode != 0 and "whole input" in p.stderr
+
+
+def test_reference_format_forced_above_one_mib(w3, tmp_path, libs):
+    """-r 1: the reference's own one-stream file whatever the size (one block here), readable by the
+    reference; without it a file above 1 MiB goes into the w3Bk container."""
+    data = w3_corpus.generate((2 << 20) + 12345, offset=77)
+    (tmp_path / "big.txt").write_bytes(data)
+    run(w3, tmp_path, "-r", "1", "c", "big.txt")
+    blob = (tmp_path / "big.bin").read_bytes()
+    assert blob[:4] == b"w30i" and blob == libs.oracle.compress_file(data)
+    run(w3, tmp_path, "d", "big.bin")
+    assert (tmp_path / "big.orig").read_bytes() == data
+    run(w3, tmp_path, "c", "big.txt")
+    assert (tmp_path / "big.bin").read_bytes()[:4] == b"w3Bk"

@@ -60,12 +60,15 @@ static int fail(const char *what, int rc) {
 }
 static void usage() { /* main.rs:154-161 */
   fprintf(stderr,
-          "Usage: w3 [-b block_bytes] [-g gpus] [-m book1|enwik7|train] [-w window_bytes] <action> <path>\n"
-          "  action: c (compress) | d (decompress) | t (test)\n");
+          "Usage: w3 [-b block_bytes] [-g gpus] [-m book1|enwik7|train] [-w window_bytes] [-r 1] <action> <path>\n"
+          "  action: c (compress) | d (decompress) | t (test)\n"
+          "  -r 1: always write the reference's own file format (w30i: one stream = one block, at most 256 MiB);\n"
+          "        without it files above 1 MiB go into the w3Bk block container, which the reference cannot read\n");
   exit(1);
 }
 
 static size_t g_block = 0;
+static bool g_reference_format = false; /* -r 1 */
 static size_t g_window = 0; /* 0: whole file in memory */
 static std::string g_model = "book1";
 
@@ -179,7 +182,7 @@ static int do_compress(w3_ctx *ctx, const std::string &in, const std::string &ou
     if (mrc == W3_OK) mrc = w3_ctx_set_model(ctx, table);
     if (mrc != W3_OK) return fail("model", mrc);
   }
-  bool legacy = g_model == "book1" && g_block == 0 && data.size() <= W3_DEFAULT_BLOCK;
+  bool legacy = g_model == "book1" && g_block == 0 && (g_reference_format || data.size() <= W3_DEFAULT_BLOCK);
   size_t bs = g_block ? g_block : W3_DEFAULT_BLOCK;
   std::vector<uint8_t> buf(data.size() + data.size() / 4 + 4096);
   size_t len = 0;
@@ -242,6 +245,7 @@ int main(int argc, char **argv) {
     if (!strcmp(argv[i], "-b")) g_block = strtoull(argv[i + 1], nullptr, 0);
     else if (!strcmp(argv[i], "-g")) gpus = atoi(argv[i + 1]);
     else if (!strcmp(argv[i], "-w")) g_window = strtoull(argv[i + 1], nullptr, 0);
+    else if (!strcmp(argv[i], "-r")) g_reference_format = atoi(argv[i + 1]) != 0;
     else if (!strcmp(argv[i], "-m") && (!strcmp(argv[i + 1], "book1") || !strcmp(argv[i + 1], "enwik7") || !strcmp(argv[i + 1], "train"))) g_model = argv[i + 1];
     else usage();
   }
