@@ -434,11 +434,17 @@ static bool geo_ok(int ctx_bits, int align_bits, int max_bits) {
   return ctx_bits >= 1 && ctx_bits <= 30 && align_bits >= 0 && align_bits <= 7 && align_bits <= ctx_bits &&
          max_bits >= 1 && max_bits <= 32;
 }
-/* blocks of one batch: the hash array costs 32 bytes per input byte, the counters 4 << ctx_bits per block */
-static size_t geo_batch_blocks(size_t bs, int ctx_bits, bool with_hash) {
-  size_t by_cnt = std::max<size_t>(1, ((size_t)16 << 30) / ((size_t)4 << ctx_bits));
-  size_t by_h = with_hash ? std::max<size_t>(1, ((size_t)8 << 30) / (32 * bs)) : by_cnt;
-  return std::min<size_t>(std::min(by_cnt, by_h), 4096);
+/* blocks of one batch: the hash array costs 32 bytes per input byte, the counters 4 << ctx_bits per
+ * block; a batch takes up to 40 % / 30 % of the device's free memory for them (every block of a batch
+ * is one stream in flight: the more, the better the gathers overlap) */
+static size_t geo_batch_blocks(const w3_dev &d, size_t bs, int ctx_bits, bool with_hash) {
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = (size_t)32 << 30;
+  free_b += d.geo_H.cap + d.geo_counters.cap; /* what this path already holds is reusable */
+  const size_t h_budget = std::max<size_t>((size_t)2 << 30, free_b / 10 * 4), c_budget = std::max<size_t>((size_t)2 << 30, free_b / 10 * 3);
+  size_t by_cnt = std::max<size_t>(1, c_budget / ((size_t)4 << ctx_bits));
+  size_t by_h = with_hash ? std::max<size_t>(1, h_budget / (32 * bs)) : by_cnt;
+  return std::min<size_t>(std::min(by_cnt, by_h), 8192);
 }
 
 /* encode blocks [b0, b1) of `in` on device g with the context's geometry; same contract as encode_part */
@@ -453,7 +459,7 @@ static int encode_part_geo(w3_ctx *ctx, int g, const uint8_t *in, size_t n, size
   int rc;
   if ((rc = d.in.ensure(round_up(bytes, 4) + 16)) != W3_OK) return rc;
   CK(cudaMemcpyAsync(d.in.p, in + off, bytes, cudaMemcpyHostToDevice, d.stream));
-  const size_t per = geo_batch_blocks(bs, ctx->ctx_bits, true);
+  const size_t per = geo_batch_blocks(d, bs, ctx->ctx_bits, true);
   const size_t nbat = std::min(per, nb);
   size_t stride = round_up(bs + (bs >> 3) + 64, 16);
   if ((rc = d.geo_H.ensure(nbat * bs * 32 + 64)) != W3_OK) return rc;
@@ -523,7 +529,7 @@ static int decode_part_geo(w3_ctx *ctx, int g, const uint8_t *streams, const std
   int rc;
   if ((rc = d.packed.ensure(clen + 16)) != W3_OK) return rc;
   if ((rc = d.out.ensure(round_up(obytes, 4) + 16)) != W3_OK) return rc;
-  const size_t nbat = std::min(geo_batch_blocks(bs, ctx_bits, false), nbg);
+  const size_t nbat = std::min(geo_batch_blocks(d, bs, ctx_bits, false), nbg);
   if ((rc = d.geo_counters.ensure(nbat * ((size_t)4 << ctx_bits))) != W3_OK) return rc;
   if ((rc = d.geo_jobs.ensure(nbat * sizeof(w3_geo_job))) != W3_OK) return rc;
   if (clen) CK(cudaMemcpyAsync(d.packed.p, streams + c0, clen, cudaMemcpyHostToDevice, d.stream));

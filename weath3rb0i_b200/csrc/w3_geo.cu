@@ -101,20 +101,29 @@ __global__ void w3_k_geo_encode(w3_geo_job *__restrict__ jobs, uint32_t n_jobs, 
     else ovf = 1;
   };
   const bool count_only = job.out == nullptr;
+  /* The contexts are known in advance (H), so the counter of position t + 2 is loaded while position t
+   * is coded: two gathers in flight per stream.  A counter loaded early is stale if one of the two
+   * positions in between used the same context — then the value they wrote is forwarded instead. */
+  auto ctx_at = [&](uint32_t t) -> uint32_t { return w3_geo_ctx(__ldg(H + t), t, job.ctx_bits, job.align_bits); };
+  uint32_t ctx0 = nbits > 0u ? ctx_at(0u) : 0u, ctx1 = nbits > 1u ? ctx_at(1u) : 0u; /* contexts of t, t + 1 */
+  uint32_t c0 = cnt[ctx0], c1 = cnt[ctx1];                                            /* their counters as loaded */
+  uint32_t pctx1 = 0xFFFFFFFFu, pnv1 = 0u, pctx2 = 0xFFFFFFFFu, pnv2 = 0u;            /* what t - 1 and t - 2 wrote */
   for (uint32_t i = 0; i < job.nbytes; i++) {
     const uint32_t byte = job.in[i];
 #pragma unroll 1
     for (uint32_t kb = 0; kb < 8u; kb++) {
       const uint32_t t = i * 8u + kb;
-      if (t + W3_GEO_PF < nbits) { /* the context W3_GEO_PF positions ahead is known: pull its counter into L2 */
-        const uint32_t cp = w3_geo_ctx(__ldg(H + t + W3_GEO_PF), t + W3_GEO_PF, job.ctx_bits, job.align_bits);
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(cnt + cp));
-      }
+      if (t + W3_GEO_PF < nbits) /* further ahead, pull the line into L2 */
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(cnt + ctx_at(t + W3_GEO_PF)));
+      const uint32_t ctx2 = t + 2u < nbits ? ctx_at(t + 2u) : 0u;
+      const uint32_t c2 = cnt[ctx2]; /* issued now, used two positions on */
       const uint32_t bit = (byte >> (7u - kb)) & 1u;
-      const uint32_t ctx = w3_geo_ctx(__ldg(H + t), t, job.ctx_bits, job.align_bits);
-      const uint32_t c = cnt[ctx];
+      const uint32_t c = ctx0 == pctx1 ? pnv1 : ctx0 == pctx2 ? pnv2 : c0;
       const uint32_t p = w3_counter_p1(c & 0xFFFFu, c >> 16); /* predict — main.rs:105 */
-      cnt[ctx] = w3_counter_update(c, bit);                   /* adapt — main.rs:106 */
+      const uint32_t nv = w3_counter_update(c, bit);          /* adapt — main.rs:106 */
+      cnt[ctx0] = nv;
+      pctx2 = pctx1; pnv2 = pnv1; pctx1 = ctx0; pnv1 = nv;
+      ctx0 = ctx1; c0 = c1; ctx1 = ctx2; c1 = c2;
       w3_ac_narrow(x1, x2, bit, p << 16);                     /* encode — main.rs:107 */
       const uint32_t pre = x1;
       int s, k;
