@@ -95,8 +95,7 @@ W3_HD uint32_t w3_cm_find_slot(uint8_t *cell, uint64_t hash, const uint8_t *bits
   const uint32_t sh = 12u * (3u - victim);
   hc = (hc & ~((uint64_t)0xFFFu << sh)) | (chk << sh);
   for (uint32_t i = 0; i < W3_CELL_HASH_BYTES; i++) cell[i] = (uint8_t)(hc >> (8u * (5u - i)));
-  for (uint32_t bit_id = 0; bit_id < 4u; bit_id++)
-    for (uint32_t c = 0; c < (1u << bit_id); c++) w3_slot_set_state(cell, victim, bit_id, c, 0u);
+  w3_slot_clear(cell, victim); /* = Slot::set_state(bit_id, nib_ctx, 0) for all 15 states, as the oracle spells it */
   return victim;
 }
 /* one weight's training step */

@@ -143,6 +143,20 @@ W3_HD void w3_slot_get_nib(const uint8_t *cell, uint32_t id, uint32_t nib, uint1
   s[3] = (uint16_t)w3_slot_get_state(cell, id, 3u, nib >> 1);
 }
 
+/* all 15 states of a slot to 0 — what 15 Slot::set_state(.., 0) calls leave behind, in 24 byte
+ * stores: slot id holds bits [180 id, 180 id + 180) of slots[]; odd slots start, even slots end,
+ * on a half byte shared with their neighbour (docs/hashslots.md:136-139) */
+W3_HD void w3_slot_clear(uint8_t *cell, uint32_t id) {
+  uint8_t *p = cell + W3_CELL_HASH_BYTES + (id * 45u >> 1); /* byte 0, 22, 45, 67 */
+  if (id & 1u) {
+    p[0] &= 0xF0u;
+    for (uint32_t i = 1; i <= 22u; i++) p[i] = 0;
+  } else {
+    for (uint32_t i = 0; i < 22u; i++) p[i] = 0;
+    p[22] &= 0x0Fu;
+  }
+}
+
 /* OpinionMixer2::mix (src/mixers/opinion_mixer2.rs:5-10): the more confident of two probabilities */
 W3_HD uint32_t w3_opinion_mix2(uint32_t p1, uint32_t p2) {
   const uint32_t d1 = p1 >= 0x8000u ? p1 - 0x8000u : 0x8000u - p1;
