@@ -172,6 +172,31 @@ def test_hostile_inputs(ctx, libs):
         assert ctx.decompress(blob) == data
 
 
+def test_overflowed_blocks_are_recoded_alone(ctx, libs):
+    """A stream that does not fit its scratch region is measured, not stored, and only those blocks
+    are coded again into regions of exactly their size.  With the first-pass region cut to half a
+    block, text fits (ratio 0.45) and the random and all-ones... blocks do not."""
+    import random as _r
+
+    rnd = _r.Random(77)
+    block = 8192
+    parts = []
+    for i in range(12):
+        parts.append(bytes(rnd.getrandbits(8) for _ in range(block)) if i in (2, 3, 9) else w3_corpus.generate(block, offset=i * block))
+    data = b"".join(parts) + w3_corpus.generate(1000)
+    want = ctx.compress(data, block)
+    ctx.set_option(capi.W3_OPT_SCRATCH_PERMILLE, 500)
+    try:
+        got = ctx.compress(data, block)
+    finally:
+        ctx.set_option(capi.W3_OPT_SCRATCH_PERMILLE, 0)
+    assert got == want
+    _, _, streams = split_container(got)
+    for i in (1, 2, 9, 12):
+        assert streams[i] == libs.oracle.compress_block(data[i * block : (i + 1) * block]), i
+    assert ctx.decompress(got) == data
+
+
 def test_truncated_legacy_stream_zero_pads(ctx, libs):
     """ACReader yields 0 bits past EOF (io.rs:23-25): a cut file still decodes
     `len` bytes, identically to the reference algorithm."""

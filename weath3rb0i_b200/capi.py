@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("W3_LIB") or os.path.join(HERE, "libw3codec.so")  # W3_LIB: another build of the same library
 
 W3_OK, W3_E_ARG, W3_E_CAP, W3_E_MAGIC, W3_E_CUDA, W3_E_FORMAT, W3_E_TABLE, W3_E_TOOBIG = 0, -1, -2, -3, -4, -5, -6, -7
-W3_OPT_KERNELS, W3_OPT_ENC_TEAMS, W3_OPT_LANE_WARPS, W3_OPT_LANE_FORM, W3_OPT_ENC_CODER = 1, 2, 3, 4, 5
+W3_OPT_KERNELS, W3_OPT_ENC_TEAMS, W3_OPT_LANE_WARPS, W3_OPT_LANE_FORM, W3_OPT_ENC_CODER, W3_OPT_SCRATCH_PERMILLE = 1, 2, 3, 4, 5, 6
 KERNELS = {"auto": 0, "team": 1, "warp": 2, "many": 3}
 W3_F_LEGACY = 1
 DEFAULT_BLOCK = 1 << 20

@@ -111,7 +111,7 @@ struct w3_ctx {
   int n = 0;
   w3_dev d[W3_MAX_DEVICES];
   uint16_t table[8]; /* the StationaryModel in force (init_model: for_book1, src/main.rs:151) */
-  w3_launch_opts opts = {0, 0, 0, 0, 0}; /* w3_ctx_set_option */
+  w3_launch_opts opts = {0, 0, 0, 0, 0, 0}; /* w3_ctx_set_option */
   /* OrderNEntropy::new(bits_in_context, alignment_bits, ACHistory::new(max_bits, ..)); init_model: 11, 3, 8 */
   int ctx_bits = W3_CTX_BITS, align_bits = W3_ALIGN_BITS, max_bits = W3_HASH_BITS;
   bool default_geometry() const { return ctx_bits == W3_CTX_BITS && align_bits == W3_ALIGN_BITS && max_bits == W3_HASH_BITS; }
@@ -275,6 +275,7 @@ int w3_ctx_set_option(w3_ctx *ctx, int option, int value) {
     case W3_OPT_KERNELS: if (value > 3) return W3_E_ARG; ctx->opts.kernels = value; return W3_OK;
     case W3_OPT_ENC_TEAMS: if (value > 8) return W3_E_ARG; ctx->opts.enc_teams = value; return W3_OK;
     case W3_OPT_LANE_WARPS: if (value > 8) return W3_E_ARG; ctx->opts.lane_warps = value; return W3_OK;
+    case W3_OPT_SCRATCH_PERMILLE: if (value && (value < 10 || value > 20000)) return W3_E_ARG; ctx->opts.scratch_permille = value; return W3_OK;
     case W3_OPT_ENC_CODER: if (value > 1) return W3_E_ARG; ctx->opts.enc_coder = value; return W3_OK;
     case W3_OPT_LANE_FORM: if (value > 3) return W3_E_ARG; ctx->opts.lane_form = value; return W3_OK;
     default: return W3_E_ARG;
@@ -384,6 +385,7 @@ static int encode_part(w3_ctx *ctx, int g, const uint8_t *in, size_t n, size_t b
    * the cost of a bit at 16 + eps bits), so only the blocks that overflowed are coded again, each
    * into a region of exactly the size it asked for. */
   size_t stride = round_up(bs + (bs >> 3) + 64, 16);
+  if (ctx->opts.scratch_permille) stride = round_up(bs / 1000 * (size_t)ctx->opts.scratch_permille + bs % 1000 + 16, 16);
   if ((rc = d.scratch.ensure(stride * nb)) != W3_OK) return rc;
   CK(cudaMemsetAsync(d.d_flag, 0, 4, d.stream));
   CK(w3_launch_encode((const uint8_t *)d.in.p, bytes, (uint32_t)bs, (uint32_t)nb,

@@ -14,6 +14,7 @@ struct w3_launch_opts {
   int enc_teams;  /* W3_OPT_ENC_TEAMS: teams per CTA of the team encoder, 0 auto */
   int lane_warps; /* W3_OPT_LANE_WARPS: warps per CTA of the lane decoder, 0 auto */
   int enc_coder;  /* W3_OPT_ENC_CODER: 0 auto (one coder warp per CTA from two teams on), 1 a coder warp per team */
+  int scratch_permille; /* W3_OPT_SCRATCH_PERMILLE: first-pass scratch region per block in 1/1000 of the block size; 0 = 1125 */
   int lane_form;  /* W3_OPT_LANE_FORM: 0 auto, 1 one lane per block, 2 a pair of lanes per block, 3 pair + probability table */
 };
 
