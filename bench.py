@@ -291,7 +291,15 @@ def run_b200(args):
     # ---- end to end: host buffers through the C ABI, ONE container joined in shared host memory ----
     hdr_total = sharding.HDR_BLOCKS + 4 * nb_total
     shm_cap = hdr_total + n_total + n_total // 8 + 64 * (nb_total + 1)
-    shm_path = f"/dev/shm/w3_bench_{os.environ.get('MASTER_PORT', 'solo')}_{os.getuid()}.w3bk"
+    shm_dir = "/dev/shm"
+    try:  # shared host memory for the joined container; a plain temporary directory if /dev/shm is too small
+        import shutil
+        if shutil.disk_usage(shm_dir).free < shm_cap + (64 << 20):
+            raise OSError("small /dev/shm")
+    except OSError:
+        import tempfile
+        shm_dir = tempfile.gettempdir()
+    shm_path = os.path.join(shm_dir, f"w3_bench_{os.environ.get('MASTER_PORT', 'solo')}_{os.getuid()}.w3bk")
     if rank == 0:
         with open(shm_path, "wb") as f:
             f.truncate(shm_cap)

@@ -127,6 +127,7 @@ w3_cm_blocks(const uint8_t *__restrict__ src, const uint64_t *__restrict__ offse
       }
       __syncwarp();
       uint32_t nib_ctx = 0;
+#pragma unroll
       for (uint32_t j = 0; j < 4u; j++) {
         const uint32_t sel = nb * 4u + j;
         /* ---- predict ------------------------------------------------------------------------ */
