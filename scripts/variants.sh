@@ -10,7 +10,7 @@ if [ "$1" = build ]; then
   for v in "$@"; do
     name=${v%%:*}; flags=${v#*:}
     nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall $flags \
-      -shared -o tools/variants/$name.so weath3rb0i_b200/csrc/w3_kernels.cu weath3rb0i_b200/csrc/w3_tierb.cu weath3rb0i_b200/csrc/w3_geo.cu weath3rb0i_b200/csrc/w3_capi.cu 2>&1 | grep -E "error" &
+      -shared -o tools/variants/$name.so weath3rb0i_b200/csrc/w3_kernels.cu weath3rb0i_b200/csrc/w3_tierb.cu weath3rb0i_b200/csrc/w3_geo.cu weath3rb0i_b200/csrc/w3_cm.cu weath3rb0i_b200/csrc/w3_capi.cu 2>&1 | grep -E "error" &
   done
   wait; ls tools/variants
 elif [ "$1" = many ]; then
