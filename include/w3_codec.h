@@ -59,13 +59,14 @@ int w3_ctx_device_count(const w3_ctx *ctx);
 #define W3_OPT_KERNELS 1    /* 0 auto | 1 team: one CTA per block | 2 warp: one warp per block (round 1)
                                | 3 many-block: teams sharing a CTA (encode), one lane per block (decode) */
 #define W3_OPT_ENC_TEAMS 2  /* blocks per CTA of the team encoder, 1..8; 0 auto */
-#define W3_OPT_LANE_WARPS 3 /* warps per CTA of the lane decoder, 1..8 (split form: blocks per CTA, 1..16); 0 auto */
+#define W3_OPT_LANE_WARPS 3 /* warps per CTA of the lane decoder, 1..8 (split form, when asked for: blocks per CTA); 0 auto */
 #define W3_OPT_ENC_CODER 5  /* team encoder with several teams per CTA: 0 one coder warp per CTA (lane b codes team b) | 1 one per team */
 #define W3_OPT_SCRATCH_PERMILLE 6 /* first-pass stream region per block, in 1/1000 of the block size (0 = the default 1125):
                                      a test hook for the path that re-encodes the blocks whose stream did not fit */
 #define W3_OPT_LANE_FORM 4  /* lane decoder: 0 auto | 1 one lane per block | 2 two lanes per block (speculating the next
                                context) | 3 the same with a probability table next to the counters | 4 split: a coder warp
-                               and two model warps per group of blocks */
+                               and eight model warps per CTA of up to 8 blocks.  0 = split when an SM gets at most 8 blocks,
+                               else two lanes per block */
 int w3_ctx_set_option(w3_ctx *ctx, int option, int value);
 
 /* ---- the StationaryModel of the entropy hash -------------------------------

@@ -53,18 +53,25 @@ def pick(m):
 
 def main():
     res, bench = {}, {}
-    reps = {"decode_pair": "r02_prof_decode_pair", "encode_team": "r02_prof_encode_team", "gather_probe": "r02_prof_gather_probe",
-            "hbm_paths": "r02_prof_hbm_paths"}
+    reps = {"decode_split": "r02_prof_decode_split", "decode_pair": "r02_prof_decode_pair", "encode_team": "r02_prof_encode_team",
+            "gather_probe": "r02_prof_gather_probe", "hbm_paths": "r02_prof_hbm_paths"}
+    prev = {}
+    try:  # captures made earlier in the round stay as they are when their reports are no longer here
+        prev = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_metrics.json")))
+    except (OSError, ValueError):
+        pass
     for name, f in reps.items():
         rep = os.path.join(OUT, f + ".ncu-rep")
         if not os.path.exists(rep):
             print("missing", rep)
+            if name in prev.get("details", {}):
+                res[name] = prev["details"][name]
             continue
         rows = [pick(m) for m in raw_rows(rep)]
         res[name] = rows if len(rows) > 1 else (rows[0] if rows else {})
     # what bench.py wants: per-kernel DRAM bytes and warp instructions per launch on the 1 GiB workload
     n = 1 << 30
-    for key, kn in (("decode_pair", "w3_decode_blocks_pair"), ("encode_team", "w3_encode_blocks_team")):
+    for key, kn in (("decode_split", "w3_decode_blocks_split"), ("decode_pair", "w3_decode_blocks_pair"), ("encode_team", "w3_encode_blocks_team")):
         m = res.get(key)
         if isinstance(m, dict) and m:
             bench[kn] = {"input_bytes": n,

@@ -272,8 +272,6 @@ class HostSim:
         h.hs_lane_decode_block.argtypes = [C.c_void_p, C.c_char_p, sz, C.c_uint, C.c_uint8, C.c_void_p, sz, C.c_int]
         h.hs_pair_decode_block.argtypes = [C.c_void_p, C.c_char_p, sz, C.c_uint, C.c_uint8, C.c_void_p, sz, C.c_int]
         h.hs_split_decode_block.argtypes = [C.c_void_p, C.c_char_p, sz, C.c_uint, C.c_uint8, C.c_void_p, sz, C.c_int]
-        h.hs_ahead_decode_block.argtypes = [C.c_void_p, C.c_char_p, sz, C.c_uint, C.c_uint8, C.c_void_p, sz, C.c_int]
-        h.hs_lt_decode_block.argtypes = [C.c_void_p, C.c_char_p, sz, C.c_uint, C.c_uint8, C.c_void_p, sz, C.c_int]
         self.lib = h
         self.table = (C.c_uint16 * 8)(*table)
         self.max_bits = max_bits
@@ -306,17 +304,13 @@ class HostSim:
         """w3_lane.cuh's per-lane decoder (what w3_decode_blocks_lane runs in every lane), or its
         pair form (w3_decode_blocks_pair: two lanes per block in lockstep; pair="cache" = with the
         probability table), or the split form (pair="split": w3_decode_blocks_split's coder lane and
-        model lanes of a block)."""
+        the model lanes of a block as actors in a random order; the schedule's seed varies with the call)."""
         out = C.create_string_buffer(max(n_out, 1))
         fn = self.lib.hs_pair_decode_block if pair else self.lib.hs_lane_decode_block
-        if pair == "split":
-            fn = self.lib.hs_split_decode_block
         flag = 1 if pair == "cache" else 0
-        if pair in ("ahead2", "ahead4"):  # w3_decode_blocks_ahead<2 | 4>: the models guess two bits
-            fn, flag = self.lib.hs_ahead_decode_block, int(pair[-1])
-        if pair in ("lt4", "lt8"):  # w3_decode_blocks_lt<4 | 8>: the elastic form; the schedule's seed varies with the call
-            self._lt_seed = getattr(self, "_lt_seed", 0) + 1
-            fn, flag = self.lib.hs_lt_decode_block, int(pair[-1]) | (self._lt_seed << 4)
+        if pair == "split":
+            self._split_seed = getattr(self, "_split_seed", 0) + 1
+            fn, flag = self.lib.hs_split_decode_block, self._split_seed
         rc = fn(self.tab, stream, len(stream), misalign, junk, out, n_out, flag)
         assert rc == 0, rc
         return out.raw[:n_out]

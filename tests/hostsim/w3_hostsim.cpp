@@ -292,81 +292,17 @@ static int hs_pair_decode(const w3_hashtab *tab, const uint8_t *in, size_t n_in,
   }
   return cnt0 == cnt1 ? 0 : -2;
 }
-/* the split form (w3_decode_blocks_split): the coder warp's lane and the two lanes of each model warp
- * that serve one block, stepped in the order the ring words allow on the device — coder step t, then
- * the model warp of t's parity.  The ring is modelled with its tags: a read whose tag does not match
- * is a failure here (on the device it would be a wait). */
+/* the split form (w3_decode_blocks_split): one block's coder lane and its four lanes in each of the eight model
+ * warps, as independent actors scheduled at random (seeded): whatever the interleaving, the sequence numbers in
+ * the ring words must keep the result right.  An actor whose word is not there yet does nothing (on the device it
+ * polls).  Returns -6 if nothing can move any more (a deadlock). */
 static int hs_split_decode(const w3_hashtab *tab, const uint8_t *in, size_t n_in, unsigned misalign,
-                           uint8_t junk, uint8_t *out, size_t n_out) {
+                           uint8_t junk, uint8_t *out, size_t n_out, uint32_t seed) {
   hs_lane_env env(tab, in, n_in, misalign, junk);
   const uint32_t sh = (uint32_t)((uintptr_t)env.sp & 3u);
   const uint32_t *ab = (const uint32_t *)(env.sp - sh);
   const uint32_t bp0 = sh * 8u, end_bits = bp0 + (uint32_t)n_in * 8u;
-  std::vector<uint32_t> cnt[2] = {std::vector<uint32_t>(W3_NCTX, 0u), std::vector<uint32_t>(W3_NCTX, 0u)}; /* per lane of a pair */
-  const w3_lane_mem m[2] = {env.mem(cnt[0].data(), tab), env.mem(cnt[1].data(), tab)};
-  uint32_t ring_cand[W3_SPLIT_CAND_SLOTS][2] = {}, ring_bits[W3_SPLIT_BIT_SLOTS] = {};
-  w3_split_mod mod[2][2]; /* [parity][g] */
-  for (uint32_t par = 0; par < 2; par++)
-    for (uint32_t g = 0; g < 2; g++) {
-      w3_split_mod &s = mod[par][g];
-      s.khi = s.klo = 0u;
-      s.cand_ci = W3_CTX0_RANKED * 4u;
-      if (par == 0) ring_cand[0][g] = 0x80000000u | w3_split_cand_tag(0u);
-    }
-  /* the odd warp's first candidate reads counters both lanes still agree on (all zero) */
-  for (uint32_t g = 0; g < 2; g++) ring_cand[1][g] = w3_split_guess(mod[1][g], g, 1u, m[g]) | w3_split_cand_tag(1u);
-  w3_lane_coder c;
-  w3_lane_coder_init(c, ab, bp0, end_bits);
-  uint32_t prev = 0;
-  for (size_t i = 0; i < n_out; i++) {
-    uint32_t byte = 0;
-    const bool fast = c.bp + W3_LANE_FAST_MARGIN <= end_bits;
-    for (uint32_t a = 0; a < 8u; a++) {
-      const uint32_t t = 8u * (uint32_t)i + a;
-      /* coder warp */
-      const uint32_t w = ring_cand[a & 3u][prev];
-      if ((w & 0xFFu) != w3_split_cand_tag(t)) return -3;
-      uint32_t mm;
-      const uint32_t bit = w3_lane_coder_bit(c, w & 0xFFFF0000u, mm);
-      ring_bits[a] = bit | w3_split_bit_tag(t);
-      if (fast) w3_lane_coder_shift<false>(c, bit, mm, ab, end_bits, 0xFFFFFFFFu);
-      else w3_lane_coder_shift<true>(c, bit, mm, ab, end_bits, 0xFFFFFFFFu);
-      prev = bit;
-      byte = (byte << 1) | bit;
-      /* model warp of t's parity */
-      const uint32_t par = a & 1u;
-      uint32_t b1 = 0u;
-      if (t > 0u) {
-        const uint32_t w1 = ring_bits[(a + 7u) & 7u];
-        if ((w1 & 0xFFFF0000u) != w3_split_bit_tag(t - 1u)) return -4;
-        b1 = w1 & 1u;
-      }
-      const uint32_t ci_t = mod[par][b1].cand_ci; /* the shuffle */
-      const uint32_t w0 = ring_bits[a];
-      if ((w0 & 0xFFFF0000u) != w3_split_bit_tag(t)) return -5;
-      const uint32_t b0 = w0 & 1u;
-      for (uint32_t g = 0; g < 2; g++) {
-        w3_split_mod &s = mod[par][g];
-        if (t > 0u) w3_split_take(s, b1);
-        w3_split_take(s, b0);
-        ring_cand[(a + 2u) & 3u][g] = w3_split_guess(s, g, (a + 2u) & 7u, m[g]) | w3_split_cand_tag(t + 2u);
-        w3_split_adapt(ci_t, b0, m[g]);
-      }
-    }
-    out[i] = (uint8_t)byte;
-  }
-  return cnt[0] == cnt[1] ? 0 : -2;
-}
-/* the split form two bits ahead (w3_decode_blocks_ahead<kNB>): the coder lane and the four lanes a block has
- * in each of the kNB model warps.  Order: activations for positions 0..2 (they wait for nothing), then
- * coder step t followed by the activation for position t + 3 (which waited for bit t). */
-template <uint32_t kNB>
-static int hs_ahead_decode(const w3_hashtab *tab, const uint8_t *in, size_t n_in, unsigned misalign,
-                           uint8_t junk, uint8_t *out, size_t n_out) {
-  hs_lane_env env(tab, in, n_in, misalign, junk);
-  const uint32_t sh = (uint32_t)((uintptr_t)env.sp & 3u);
-  const uint32_t *ab = (const uint32_t *)(env.sp - sh);
-  const uint32_t bp0 = sh * 8u, end_bits = bp0 + (uint32_t)n_in * 8u;
+  const uint32_t nbits = 8u * (uint32_t)n_out, blk = 3u; /* any column of the rings */
   std::vector<uint32_t> cnt[4]; /* per lane of the block's four */
   w3_lane_mem m[4];
   for (uint32_t g = 0; g < 4; g++) {
@@ -374,85 +310,8 @@ static int hs_ahead_decode(const w3_hashtab *tab, const uint8_t *in, size_t n_in
     for (size_t i = W3_NCTX; i < 2 * W3_NCTX; i++) cnt[g][i] = 0x80000000u;
     m[g] = env.mem(cnt[g].data(), tab);
   }
-  uint32_t ring_cand[W3_AHEAD_SLOTS][4] = {}, ring_bits[W3_AHEAD_SLOTS] = {};
-  w3_ahead_mod<kNB> mod[kNB][4];
-  for (uint32_t w = 0; w < kNB; w++)
-    for (uint32_t g = 0; g < 4; g++) w3_ahead_init(mod[w][g]);
-  int rc = 0;
-  auto activate = [&](uint32_t q) {
-    const uint32_t W = q % kNB, a = q & 7u;
-    uint32_t v = 0u;
-    if (kNB == 4u && q >= 5u) {
-      const uint32_t w = ring_bits[(q - 5u) & 7u];
-      if ((w & 0xFFFF0000u) != w3_split_bit_tag(q - 5u)) rc = -4;
-      v = w & 3u;
-    }
-    if (q >= 3u) {
-      const uint32_t w = ring_bits[(q - 3u) & 7u];
-      if ((w & 0xFFFF0000u) != w3_split_bit_tag(q - 3u)) rc = -5;
-      v = kNB == 4u ? v | ((w & 3u) << 2) : (w & 3u);
-    }
-    uint32_t ci_new[4], ci_old[4], pick[4], bit[4];
-    for (uint32_t g = 0; g < 4; g++) {
-      ci_new[g] = W3_CTX0_RANKED * 4u;
-      uint32_t P = 0x80000000u;
-      if (q != 0u) P = w3_ahead_guess<kNB>(mod[W][g], v, g, a, m[g], ci_new[g]);
-      ring_cand[q & 7u][g] = P | w3_ahead_cand_tag(q);
-      w3_ahead_adapt_args<kNB>(mod[W][g], v, pick[g], bit[g]);
-    }
-    for (uint32_t g = 0; g < 4; g++) ci_old[g] = mod[W][pick[g]].ci[4u / kNB - 1u]; /* the shuffle */
-    for (uint32_t g = 0; g < 4; g++) {
-      if (q >= 4u) w3_ahead_adapt(ci_old[g], bit[g], m[g]);
-      w3_ahead_rotate<kNB>(mod[W][g], v, ci_new[g]);
-    }
-  };
-  for (uint32_t q = 0; q < 3u; q++) activate(q);
-  w3_lane_coder c;
-  w3_lane_coder_init(c, ab, bp0, end_bits);
-  uint32_t prev2 = 0;
-  for (size_t i = 0; i < n_out; i++) {
-    uint32_t byte = 0;
-    const bool fast = c.bp + W3_LANE_FAST_MARGIN <= end_bits;
-    for (uint32_t a = 0; a < 8u; a++) {
-      const uint32_t t = 8u * (uint32_t)i + a;
-      const uint32_t w = ring_cand[a][prev2];
-      if ((w & 0xFFu) != w3_ahead_cand_tag(t)) return -3;
-      uint32_t mm;
-      const uint32_t bit = w3_lane_coder_bit(c, w & 0xFFFF0000u, mm);
-      ring_bits[a] = (prev2 >> 1) | (bit << 1) | w3_split_bit_tag(t); /* even lane: the bit before, odd lane: this one */
-      if (fast) w3_lane_coder_shift<false>(c, bit, mm, ab, end_bits, 0xFFFFFFFFu);
-      else w3_lane_coder_shift<true>(c, bit, mm, ab, end_bits, 0xFFFFFFFFu);
-      prev2 = (prev2 >> 1) | (bit << 1);
-      byte = (byte << 1) | bit;
-      activate(t + 3u);
-      if (rc) return rc;
-    }
-    out[i] = (uint8_t)byte;
-  }
-  for (uint32_t g = 1; g < 4; g++)
-    if (cnt[g] != cnt[0]) return -2;
-  return 0;
-}
-/* the elastic split form (w3_decode_blocks_lt<kNB>): one block's coder lane and its four lanes in each of
- * the kNB model warps, as independent actors scheduled at random (seeded): whatever the interleaving, the
- * tags of the ring words must keep the result right.  Returns -6 if nothing can move (a deadlock). */
-template <uint32_t kNB>
-static int hs_lt_decode(const w3_hashtab *tab, const uint8_t *in, size_t n_in, unsigned misalign,
-                        uint8_t junk, uint8_t *out, size_t n_out, uint32_t seed) {
-  hs_lane_env env(tab, in, n_in, misalign, junk);
-  const uint32_t sh = (uint32_t)((uintptr_t)env.sp & 3u);
-  const uint32_t *ab = (const uint32_t *)(env.sp - sh);
-  const uint32_t bp0 = sh * 8u, end_bits = bp0 + (uint32_t)n_in * 8u;
-  const uint32_t nbits = 8u * (uint32_t)n_out, blk = 3u; /* any column of the rings */
-  std::vector<uint32_t> cnt[4];
-  w3_lane_mem m[4];
-  for (uint32_t g = 0; g < 4; g++) {
-    cnt[g].assign(2 * W3_NCTX, 0u);
-    for (size_t i = W3_NCTX; i < 2 * W3_NCTX; i++) cnt[g][i] = 0x80000000u;
-    m[g] = env.mem(cnt[g].data(), tab);
-  }
-  std::vector<w3_lt_ring> ringv(1);
-  memset(&ringv[0], 0, sizeof(w3_lt_ring));
+  std::vector<w3_split_ring> ringv(1);
+  memset(&ringv[0], 0, sizeof(w3_split_ring));
   const w3_sptr cand_base = (w3_sptr)&ringv[0].cand[0][0][0], pub_base = (w3_sptr)&ringv[0].pub[0][0][0];
   const w3_sptr cand_blk = cand_base + 16u * blk, pub_blk = pub_base + 8u * blk;
   auto pub_at = [&](uint32_t count, uint32_t &rh) -> bool {
@@ -460,65 +319,62 @@ static int hs_lt_decode(const w3_hashtab *tab, const uint8_t *in, size_t n_in, u
     w3_s_ld64v(pub_blk + (count & 7u) * 64u, rh, t);
     return t == count;
   };
-  w3_lt_coder c;
-  w3_lt_coder_init(c, ab, bp0, end_bits);
-  w3_lt_mod mod[kNB][4];
-  uint32_t next_q[kNB], phase[kNB]; /* phase 0: (kNB = 8) adapt of q - 8; 1: prepare q; 2: finish q */
-  for (uint32_t w = 0; w < kNB; w++) {
+  w3_lane_coder c;
+  w3_lane_coder_init(c, ab, bp0, end_bits);
+  uint32_t rhist = 0, t = 0, byte = 0;
+  w3_split_mod mod[W3_SPLIT_MODELS][4];
+  uint32_t next_q[W3_SPLIT_MODELS], phase[W3_SPLIT_MODELS]; /* 0: adapt q - 8; 1: prepare q; 2: finish q */
+  for (uint32_t w = 0; w < W3_SPLIT_MODELS; w++) {
     next_q[w] = w;
-    phase[w] = kNB == 8u ? 0u : 1u;
-    for (uint32_t g = 0; g < 4; g++) { mod[w][g].khi_prev = mod[w][g].klo = 0u; mod[w][g].ci = W3_CTX0_RANKED * 4u; }
+    phase[w] = 0u;
+    for (uint32_t g = 0; g < 4; g++) w3_split_mod_init(mod[w][g]);
   }
-  std::vector<uint32_t> dst((n_out + 3) / 4 + 1, 0u);
   uint64_t rng = seed * 0x9E3779B97F4A7C15ull + 12345u;
   uint32_t idle = 0;
-  while (c.t < nbits) {
+  while (t < nbits) {
     rng = rng * 6364136223846793005ull + 1442695040888963407ull;
-    const uint32_t actor = (uint32_t)(rng >> 33) % (kNB + (seed & 1u ? 1u : kNB)); /* odd seeds: a slow coder; even: slow models */
+    const uint32_t actor = (uint32_t)(rng >> 33) % (W3_SPLIT_MODELS + (seed & 1u ? 1u : W3_SPLIT_MODELS)); /* odd seeds: a slow coder; even: slow models */
     bool moved = false;
-    if (actor >= kNB) { /* a coder attempt */
-      const uint32_t t0 = c.t;
-      if (c.bp + (W3_LT_ATTEMPTS * 31u + 64u) <= end_bits) w3_lt_attempt<false>(c, cand_blk, pub_blk, ab, end_bits, 0xFFFFFFFFu, 0u);
-      else w3_lt_attempt<true>(c, cand_blk, pub_blk, ab, end_bits, 0xFFFFFFFFu, 0u);
-      moved = c.t != t0;
-      if ((c.t ^ t0) & 32u) {
-        const uint32_t w = w3_fsl(c.rlo, c.rhist, c.t & 31u);
-        dst[(c.t >> 5) - 1u] = w3_bswap32(w3_brev32(w));
+    if (actor >= W3_SPLIT_MODELS) { /* the coder: a step if its candidate is there */
+      const uint32_t cw = w3_s_ld32v(w3_split_cand_at(cand_blk, t, rhist));
+      if ((cw & 0xFFFFu) == w3_split_tag(t)) {
+        const uint32_t a = t & 7u;
+        uint32_t bit;
+        /* the kernel decides fast / careful per byte, for the whole warp */
+        if (a == 0u) byte = 0u;
+        if (c.bp + W3_LANE_FAST_MARGIN <= end_bits) bit = w3_split_coder_step<false>(c, rhist, t, cw, pub_blk, ab, end_bits, 0xFFFFFFFFu);
+        else bit = w3_split_coder_step<true>(c, rhist, t, cw, pub_blk, ab, end_bits, 0xFFFFFFFFu);
+        byte = (byte << 1) | bit;
+        if (a == 7u) out[t >> 3] = (uint8_t)byte;
+        t++;
+        moved = true;
       }
     } else {
       const uint32_t W = actor, q = next_q[W];
-      if (q >= nbits + 16u) { idle++; if (idle > 100000u) return -6; continue; }
       uint32_t rh = 0u;
       if (phase[W] == 0u) {
-        const bool on = q >= 8u && q - 8u < nbits;
-        if (!on || pub_at(q - 7u, rh)) {
-          if (on) {
+        if (q < 8u || pub_at(q - 7u, rh)) {
+          if (q >= 8u) {
             const uint32_t ci_old = mod[W][(rh >> 29) & 3u].ci; /* the shuffle */
-            for (uint32_t g = 0; g < 4; g++) w3_ahead_adapt(ci_old, rh >> 31, m[g]);
+            for (uint32_t g = 0; g < 4; g++) w3_split_adapt(ci_old, rh >> 31, m[g]);
           }
           phase[W] = 1u;
           moved = true;
         }
-      } else if (phase[W] == 1u) { /* prepare: both values of bit q - 3 */
-        const bool valid = q < nbits;
-        if (!(valid && q >= 3u) || pub_at(q - 3u, rh)) {
-          if (!(valid && q >= 3u)) rh = 0u;
+      } else if (phase[W] == 1u) {
+        if (q < 3u || pub_at(q - 3u, rh)) {
+          if (q < 3u) rh = 0u;
           if (q != 0u)
-            for (uint32_t g = 0; g < 4; g++) w3_lt_prepare<kNB>(mod[W][g], rh, q, g, m[g]);
-          if (kNB == 4u && valid && q >= 4u) {
-            const uint32_t ci_old = mod[W][(rh >> 29) & 3u].ci; /* the shuffle */
-            for (uint32_t g = 0; g < 4; g++) w3_ahead_adapt(ci_old, rh >> 31, m[g]);
-          }
+            for (uint32_t g = 0; g < 4; g++) w3_split_prepare(mod[W][g], rh, q, g, m[g]);
           phase[W] = 2u;
           moved = true;
         }
-      } else { /* finish */
-        const bool valid = q < nbits;
-        if (!(valid && q >= 2u) || pub_at(q - 2u, rh)) {
-          if (!(valid && q >= 2u)) rh = 0u;
-          for (uint32_t g = 0; g < 4; g++) w3_lt_finish<kNB>(mod[W][g], rh, q, g, blk, valid, cand_base);
-          next_q[W] = q + kNB;
-          phase[W] = kNB == 8u ? 0u : 1u;
+      } else {
+        if (q < 2u || pub_at(q - 2u, rh)) {
+          if (q < 2u) rh = 0u;
+          for (uint32_t g = 0; g < 4; g++) w3_split_finish(mod[W][g], rh, q, g, blk, true, cand_base);
+          next_q[W] = q + W3_SPLIT_MODELS;
+          phase[W] = 0u;
           moved = true;
         }
       }
@@ -526,29 +382,14 @@ static int hs_lt_decode(const w3_hashtab *tab, const uint8_t *in, size_t n_in, u
     idle = moved ? 0u : idle + 1u;
     if (idle > 100000u) return -6;
   }
-  const uint32_t n = (uint32_t)n_out, rem = n & 3u, hist = w3_brev32(c.rhist);
-  uint8_t *d8 = reinterpret_cast<uint8_t *>(dst.data());
-  for (uint32_t b = 0; b < rem; b++) d8[(n & ~3u) + b] = (uint8_t)(hist >> (8u * (rem - 1u - b)));
-  memcpy(out, dst.data(), n_out);
   for (uint32_t g = 1; g < 4; g++)
     if (cnt[g] != cnt[0]) return -2;
   return 0;
 }
 extern "C" {
-int hs_lt_decode_block(const w3_hashtab *tab, const uint8_t *in, size_t n_in, unsigned misalign,
-                       uint8_t junk, uint8_t *out, size_t n_out, int nb_and_seed) {
-  const uint32_t seed = (uint32_t)nb_and_seed >> 4;
-  return (nb_and_seed & 15) == 8 ? hs_lt_decode<8u>(tab, in, n_in, misalign, junk, out, n_out, seed)
-                                 : hs_lt_decode<4u>(tab, in, n_in, misalign, junk, out, n_out, seed);
-}
-int hs_ahead_decode_block(const w3_hashtab *tab, const uint8_t *in, size_t n_in, unsigned misalign,
-                          uint8_t junk, uint8_t *out, size_t n_out, int nb) {
-  return nb == 4 ? hs_ahead_decode<4u>(tab, in, n_in, misalign, junk, out, n_out)
-                 : hs_ahead_decode<2u>(tab, in, n_in, misalign, junk, out, n_out);
-}
 int hs_split_decode_block(const w3_hashtab *tab, const uint8_t *in, size_t n_in, unsigned misalign,
-                          uint8_t junk, uint8_t *out, size_t n_out, int /*unused*/) {
-  return hs_split_decode(tab, in, n_in, misalign, junk, out, n_out);
+                          uint8_t junk, uint8_t *out, size_t n_out, int seed) {
+  return hs_split_decode(tab, in, n_in, misalign, junk, out, n_out, (uint32_t)seed);
 }
 /* the pair form of the lane decoder: both lanes of a pair in lockstep, the pick (a shuffle on the
  * device) done by hand.  Each lane applies the (identical) counter update, as on the device; so

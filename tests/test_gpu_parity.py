@@ -20,16 +20,16 @@ def ctx():
     c.close()
 
 
-@pytest.fixture(params=["team", "many", "warp", "split", "ahead2", "ahead4", "lt4", "lt8"], autouse=True)
+@pytest.fixture(params=["team", "many", "warp", "pair"], autouse=True)
 def kernel_mode(request, ctx):
     """Every test runs against every kernel family (W3_OPT_KERNELS): `team` (one CTA per
     block: coder warp + model / speculator warps), `many` (the many-block regime: teams
-    sharing a CTA for encode, a lane pair per block for decode), `split` (the same with the
-    decoder's coder and model halves in different warps, W3_OPT_LANE_FORM 4) and `warp`
-    (round 1's one warp per block)."""
-    form = {"split": 4, "ahead2": 5, "ahead4": 6, "lt4": 7, "lt8": 8}.get(request.param, 0)
-    ctx.set_kernels("many" if form else request.param)
-    ctx.set_option(capi.W3_OPT_LANE_FORM, form)
+    sharing a CTA for encode; for decode the split form — a coder warp and eight model warps
+    per CTA of up to 8 blocks — as the launcher picks it for these block counts), `pair` (the
+    same with the decoder's pair form, W3_OPT_LANE_FORM 2: two lanes per block in one warp,
+    what the launcher picks beyond 8 blocks per SM) and `warp` (round 1's one warp per block)."""
+    ctx.set_kernels("many" if request.param == "pair" else request.param)
+    ctx.set_option(capi.W3_OPT_LANE_FORM, 2 if request.param == "pair" else 0)
     yield request.param
     ctx.set_option(capi.W3_OPT_LANE_FORM, 0)
     ctx.set_kernels("auto")

@@ -201,7 +201,7 @@ def test_fixed_latency_rank_lookup(libs):
 # ---- the lane decoder (w3_lane.cuh), on the CPU ------------------------------------------------
 
 
-@pytest.mark.parametrize("pair", [False, True, "cache", "split", "ahead2", "ahead4", "lt4", "lt8"], ids=["lane", "pair", "pair-cached-p", "split", "ahead2", "ahead4", "lt4", "lt8"])
+@pytest.mark.parametrize("pair", [False, True, "cache", "split"], ids=["lane", "pair", "pair-cached-p", "split"])
 @pytest.mark.parametrize("n", [0, 1, 2, 3, 4, 5, 31, 100, 4097, 70001])
 def test_lane_decoder_equals_oracle(libs, n, pair):
     """The statements every lane of w3_decode_blocks_lane / _pair executes, at every start
@@ -213,7 +213,7 @@ def test_lane_decoder_equals_oracle(libs, n, pair):
         assert libs.hostsim.lane_decode_block(stream, n, mis, junk=0xFF, pair=pair) == data, (n, mis)
 
 
-@pytest.mark.parametrize("pair", [False, True, "cache", "split", "ahead2", "ahead4", "lt4", "lt8"], ids=["lane", "pair", "pair-cached-p", "split", "ahead2", "ahead4", "lt4", "lt8"])
+@pytest.mark.parametrize("pair", [False, True, "cache", "split"], ids=["lane", "pair", "pair-cached-p", "split"])
 def test_lane_decoder_hostile_and_truncated(libs, pair):
     rnd = random.Random(17)
     cases = [bytes(rnd.getrandbits(8) for _ in range(20000)), bytes(30000), b"\xff" * 30000,
@@ -230,7 +230,7 @@ def test_lane_decoder_hostile_and_truncated(libs, pair):
             assert libs.hostsim.lane_decode_block(stream[:cut], len(data), mis, pair=pair) == want, cut
 
 
-@pytest.mark.parametrize("pair", [False, True, "cache", "split", "ahead2", "ahead4", "lt4", "lt8"], ids=["lane", "pair", "pair-cached-p", "split", "ahead2", "ahead4", "lt4", "lt8"])
+@pytest.mark.parametrize("pair", [False, True, "cache", "split"], ids=["lane", "pair", "pair-cached-p", "split"])
 def test_lane_decoder_keys_on_thresholds(libs, pair):
     """Histories that put the key exactly on a threshold (singular keys: general search) in the stream."""
     thr, _ = libs.hostsim.thresholds()

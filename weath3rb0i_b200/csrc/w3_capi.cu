@@ -274,10 +274,10 @@ int w3_ctx_set_option(w3_ctx *ctx, int option, int value) {
   switch (option) {
     case W3_OPT_KERNELS: if (value > 3) return W3_E_ARG; ctx->opts.kernels = value; return W3_OK;
     case W3_OPT_ENC_TEAMS: if (value > 8) return W3_E_ARG; ctx->opts.enc_teams = value; return W3_OK;
-    case W3_OPT_LANE_WARPS: if (value > 16) return W3_E_ARG; ctx->opts.lane_warps = value; return W3_OK;
+    case W3_OPT_LANE_WARPS: if (value > 8) return W3_E_ARG; ctx->opts.lane_warps = value; return W3_OK;
     case W3_OPT_SCRATCH_PERMILLE: if (value && (value < 10 || value > 20000)) return W3_E_ARG; ctx->opts.scratch_permille = value; return W3_OK;
     case W3_OPT_ENC_CODER: if (value > 1) return W3_E_ARG; ctx->opts.enc_coder = value; return W3_OK;
-    case W3_OPT_LANE_FORM: if (value > 8) return W3_E_ARG; ctx->opts.lane_form = value; return W3_OK;
+    case W3_OPT_LANE_FORM: if (value > 4) return W3_E_ARG; ctx->opts.lane_form = value; return W3_OK;
     default: return W3_E_ARG;
   }
 }

@@ -645,7 +645,9 @@ static inline uint32_t w3_per_cta(uint32_t n_blocks, int sm_count, uint32_t cap)
  * 109 cycles per bit with one block per SM, in as many waves as it takes.  Two waves of teams
  * (218) still beat the lanes; from the third on the lanes win.  The pair form beat the lane form
  * at every block count tried (1024 x 1 MiB: 766 against 668 MB/s; 4096 x 256 KiB: 1476 against
- * 1312), so the lane form is only used when asked for. */
+ * 1312), so the lane form is only used when asked for.  The split form (coder and models in different
+ * warps, up to 8 blocks per SM) takes ~236 cycles per bit: it takes over from the third wave of teams up
+ * to 8 blocks per SM, the pair form beyond. */
 #define W3_TEAM_MAX_WAVES 2u
 static inline uint32_t w3_lane_cap(void) { return (W3_LANE_SMEM_MAX - (uint32_t)sizeof(w3_lane_tab)) / (W3_NCTX * 4u); }
 
@@ -684,20 +686,8 @@ cudaError_t w3_kernels_init(void) {
   e = cudaFuncSetAttribute(w3_decode_blocks_pair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)(sizeof(w3_lane_tab) + (w3_lane_cap() / 2u) * W3_NCTX * 8u));
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(w3_decode_blocks_lt<4u>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)(sizeof(w3_lane_tab) + sizeof(w3_lt_ring) + W3_LT_MAXB * W3_LT_WORDS * 4u));
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(w3_decode_blocks_lt<8u>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)(sizeof(w3_lane_tab) + sizeof(w3_lt_ring) + W3_LT_MAXB * W3_LT_WORDS * 4u));
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(w3_decode_blocks_ahead<2u>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)(sizeof(w3_lane_tab) + sizeof(w3_ahead_ring) + W3_AHEAD_MAX_GROUP * W3_AHEAD_WORDS * 4u));
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(w3_decode_blocks_ahead<4u>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)(sizeof(w3_lane_tab) + sizeof(w3_ahead_ring) + W3_AHEAD_MAX_GROUP * W3_AHEAD_WORDS * 4u));
-  if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(w3_decode_blocks_split, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)(sizeof(w3_lane_tab) + sizeof(w3_split_ring) + W3_SPLIT_MAX_GROUP * W3_SPLIT_WORDS * 4u));
+                           (int)(sizeof(w3_lane_tab) + sizeof(w3_split_ring) + W3_SPLIT_MAXB * W3_SPLIT_WORDS * 4u));
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(w3_k_hash_array, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)sizeof(w3_smem_tab));
@@ -778,42 +768,20 @@ cudaError_t w3_launch_decode(const uint8_t *d_comp, const uint64_t *d_offsets, u
    * position's lookup overlapping the current bit's coder step) unless the lane form is asked for.
    * Form 3 keeps Counter::p of every counter in a second table (16 KiB per block). */
   const int form = opts ? opts->lane_form : 0;
-  if (form == 4) { /* split form: coder warp + two model warps per group of blocks */
-    uint32_t group = w3_per_cta(n_blocks, sm_count, W3_SPLIT_MAX_GROUP);
-    if (opts && opts->lane_warps > 0) group = (uint32_t)opts->lane_warps < W3_SPLIT_MAX_GROUP ? (uint32_t)opts->lane_warps : W3_SPLIT_MAX_GROUP;
+  const uint32_t q = w3_ceil_div(n_blocks, (uint32_t)sm_count);
+  /* Split form (w3_lane.cuh) when the blocks of an SM fit one CTA of it: measured on 1 GiB / 1024 blocks
+   * (profiles/r02_spin_variants.txt) 1039 ms against the pair form's 1331.  Its pace does not depend on the number of
+   * blocks in the CTA, so more than 8 per SM would mean rounds: 4096 x 256 KiB stays with the pair form. */
+  if (form == 4 || (form == 0 && q <= W3_SPLIT_MAXB)) {
+    uint32_t group = w3_per_cta(n_blocks, sm_count, W3_SPLIT_MAXB);
+    if (form == 4 && opts && opts->lane_warps > 0) group = (uint32_t)opts->lane_warps < W3_SPLIT_MAXB ? (uint32_t)opts->lane_warps : W3_SPLIT_MAXB;
     uint32_t grid = w3_ceil_div(n_blocks, group);
     if (grid > (uint32_t)sm_count) grid = (uint32_t)sm_count;
     w3_decode_blocks_split<<<grid, W3_SPLIT_THREADS, sizeof(w3_lane_tab) + sizeof(w3_split_ring) + (size_t)group * W3_SPLIT_WORDS * 4u, s>>>(
         d_comp, d_offsets, n_blocks, block_size, n_total, d_out, d_err, d_tab, group);
     return cudaGetLastError();
   }
-  if (form == 7 || form == 8) { /* elastic split form: a coder warp of attempts + 4 (form 7) or 8 (form 8) model warps */
-    uint32_t group = w3_per_cta(n_blocks, sm_count, W3_LT_MAXB);
-    if (opts && opts->lane_warps > 0) group = (uint32_t)opts->lane_warps < W3_LT_MAXB ? (uint32_t)opts->lane_warps : W3_LT_MAXB;
-    uint32_t grid = w3_ceil_div(n_blocks, group);
-    if (grid > (uint32_t)sm_count) grid = (uint32_t)sm_count;
-    const size_t smem = sizeof(w3_lane_tab) + sizeof(w3_lt_ring) + (size_t)group * W3_LT_WORDS * 4u;
-    if (form == 7)
-      w3_decode_blocks_lt<4u><<<grid, W3_LT_THREADS(4u), smem, s>>>(d_comp, d_offsets, n_blocks, block_size, n_total, d_out, d_err, d_tab, group);
-    else
-      w3_decode_blocks_lt<8u><<<grid, W3_LT_THREADS(8u), smem, s>>>(d_comp, d_offsets, n_blocks, block_size, n_total, d_out, d_err, d_tab, group);
-    return cudaGetLastError();
-  }
-  if (form == 5 || form == 6) { /* split form, two bits ahead: coder warp + 2 (form 5) or 4 (form 6) model warps */
-    uint32_t group = w3_per_cta(n_blocks, sm_count, W3_AHEAD_MAX_GROUP);
-    if (opts && opts->lane_warps > 0) group = (uint32_t)opts->lane_warps < W3_AHEAD_MAX_GROUP ? (uint32_t)opts->lane_warps : W3_AHEAD_MAX_GROUP;
-    uint32_t grid = w3_ceil_div(n_blocks, group);
-    if (grid > (uint32_t)sm_count) grid = (uint32_t)sm_count;
-    const size_t smem = sizeof(w3_lane_tab) + sizeof(w3_ahead_ring) + (size_t)group * W3_AHEAD_WORDS * 4u;
-    if (form == 5)
-      w3_decode_blocks_ahead<2u><<<grid, W3_AHEAD_THREADS(2u), smem, s>>>(d_comp, d_offsets, n_blocks, block_size, n_total, d_out, d_err, d_tab, group);
-    else
-      w3_decode_blocks_ahead<4u><<<grid, W3_AHEAD_THREADS(4u), smem, s>>>(d_comp, d_offsets, n_blocks, block_size, n_total, d_out, d_err, d_tab, group);
-    return cudaGetLastError();
-  }
-  const uint32_t q = w3_ceil_div(n_blocks, (uint32_t)sm_count);
   const bool pair = form != 1;
-  (void)q;
   const bool cache_p = pair && form == 3; /* measured slower than recomputing (profiles/r02_pair_variants.txt): on request only */
   const uint32_t cap = cache_p ? w3_lane_cap() / 2u : w3_lane_cap();
   const uint32_t per = w3_per_cta(n_blocks, sm_count, cap);
@@ -835,11 +803,6 @@ cudaError_t w3_launch_decode(const uint8_t *d_comp, const uint64_t *d_offsets, u
     w3_decode_blocks_lane<<<grid, warps * 32u, smem, s>>>(d_comp, d_offsets, n_blocks, block_size, n_total, d_out, d_err, d_tab, lanes);
   return cudaGetLastError();
 }
-
-#if W3_AHEAD_PROFILE
-cudaError_t w3_debug_ahead_prof(unsigned long long *out16) { return cudaMemcpyFromSymbol(out16, w3_ahead_prof, sizeof(w3_ahead_prof)); }
-cudaError_t w3_debug_ahead_tl(unsigned int *out) { return cudaMemcpyFromSymbol(out, w3_ahead_tl, sizeof(w3_ahead_tl)); }
-#endif
 
 cudaError_t w3_launch_train(const uint8_t *d_in, uint64_t n, uint16_t *d_cnt, uint16_t *d_table,
                             int sm_count, cudaStream_t s) {
