@@ -149,6 +149,27 @@ def test_blocks_equal_oracle_ragged(ctx, libs, block, n):
     assert ctx.decompress(blob) == data
 
 
+def test_split_decoder_group_sizes_and_rounds(ctx, kernel_mode):
+    """The split decoder (one coder warp + eight model warps per CTA, W3_OPT_LANE_FORM 4) at every
+    group size: groups the block count does not fill (lanes shadowing real blocks), a ragged last
+    block that keeps stepping past its end, and more groups than SMs (several rounds per CTA)."""
+    if kernel_mode != "many":
+        pytest.skip("one kernel family: the option pins the decoder")
+    cases = [(4096, 4096 * 37 + 4095), (256, 256 * 1300 + 1), (1024, 1024 * 300 + 7)]
+    try:
+        for block, n in cases:
+            data = w3_corpus.generate(n, offset=5)
+            ctx.set_option(capi.W3_OPT_LANE_FORM, 0)
+            blob = ctx.compress(data, block)
+            ctx.set_option(capi.W3_OPT_LANE_FORM, 4)
+            for group in (1, 2, 3, 5, 7, 8):
+                ctx.set_option(capi.W3_OPT_LANE_WARPS, group)
+                assert ctx.decompress(blob) == data, (block, n, group)
+    finally:
+        ctx.set_option(capi.W3_OPT_LANE_WARPS, 0)
+        ctx.set_option(capi.W3_OPT_LANE_FORM, 0)
+
+
 def test_empty_input(ctx, libs):
     assert ctx.compress(b"", legacy=True) == libs.oracle.compress_file(b"") == b"w30i" + bytes(8) + b"\xff"
     assert ctx.decompress(b"w30i" + bytes(8) + b"\xff") == b""
