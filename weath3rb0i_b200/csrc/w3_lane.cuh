@@ -149,15 +149,17 @@ struct w3_lane_mem {
   uint32_t ones;
 };
 
-/* rank of a key among the thresholds of alignment a, from the top 31 bits of the key */
-W3_HD uint32_t w3_lane_rank(uint32_t khi, uint32_t a, const w3_lane_mem &m, bool &bad) {
+/* rank of a key among the thresholds of alignment a, from the top 31 bits of the key; kFix thresholds looked at */
+template <int kFix>
+W3_HD uint32_t w3_lane_rank_n(uint32_t khi, uint32_t a, const w3_lane_mem &m, bool &bad) {
+  static_assert(255u + kFix <= W3_LANE_ROW, "threshold rows must cover the read-ahead");
   const uint32_t base = w3_s_ld8c(m.cellb + a * W3_LANE_NCELL + (khi >> (32u - W3_LANE_PB)));
   const w3_sptr t = m.thi31 + (a * W3_LANE_ROW + base) * 4u;
-  uint32_t b[W3_LANE_FIX];
+  uint32_t b[kFix];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-  for (int i = 0; i < W3_LANE_FIX; i++) b[i] = w3_s_ld32c(t + 4u * (uint32_t)i);
+  for (int i = 0; i < kFix; i++) b[i] = w3_s_ld32c(t + 4u * (uint32_t)i);
   /* z = key31 - threshold31 fits a signed word: > 0 the threshold is below the key, < 0 above, 0 undecided */
   const uint32_t k31 = khi >> 1;
   uint32_t above = 0;
@@ -165,14 +167,15 @@ W3_HD uint32_t w3_lane_rank(uint32_t khi, uint32_t a, const w3_lane_mem &m, bool
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-  for (int i = 0; i < W3_LANE_FIX; i++) {
+  for (int i = 0; i < kFix; i++) {
     const uint32_t z = k31 - b[i];
     above += z >> 31;
     tie |= z == 0u;
   }
   bad = tie || above == 0u; /* none above: there may be more thresholds below the key than were looked at */
-  return base + (uint32_t)W3_LANE_FIX - above;
+  return base + (uint32_t)kFix - above;
 }
+W3_HD uint32_t w3_lane_rank(uint32_t khi, uint32_t a, const w3_lane_mem &m, bool &bad) { return w3_lane_rank_n<W3_LANE_FIX>(khi, a, m, bad); }
 /* the general search, for the lane the fixed lookup declined (rare) */
 #if defined(__CUDACC__)
 __host__ __device__ __noinline__
@@ -469,6 +472,12 @@ W3_HD void w3_pair_init(w3_pair_dec &s, const uint32_t *ab, uint32_t bp0, uint32
  *
  * The model's steps are `__host__ __device__`; tests/hostsim runs coder and models as independent
  * actors in a random order, which the sequence numbers must make irrelevant. */
+#ifndef W3_SPLIT_FIX
+/* thresholds per lookup.  The pair form does best with 4 (its cost is its instruction count); here a lane that
+ * declines delays its whole warp's candidates and the coder warp polls: 6 measured 953 ms against 1013 with 4 and
+ * 959 with 8 (profiles/r02_split_fix_variants.txt) */
+#define W3_SPLIT_FIX 6
+#endif
 #define W3_SPLIT_SLOTS 8u
 #define W3_SPLIT_MAXB 8u   /* blocks per CTA: 32 model lanes / 4 guesses */
 #define W3_SPLIT_MODELS 8u /* model warps = alignments */
@@ -516,7 +525,7 @@ W3_HD void w3_split_prepare(w3_split_mod &s, uint32_t rh3, uint32_t q, uint32_t 
   const uint32_t a = q & 7u;
   const uint32_t gk0 = (rh3 >> 3) | (g << 30), gk1 = gk0 | (1u << 29);
   bool bad0, bad1;
-  uint32_t r0 = w3_lane_rank(gk0, a, m, bad0) & 255u, r1 = w3_lane_rank(gk1, a, m, bad1) & 255u; /* hash — ordern_entropy.rs:36-45 */
+  uint32_t r0 = w3_lane_rank_n<W3_SPLIT_FIX>(gk0, a, m, bad0) & 255u, r1 = w3_lane_rank_n<W3_SPLIT_FIX>(gk1, a, m, bad1) & 255u; /* hash — ordern_entropy.rs:36-45 */
   if (bad0 | bad1) {
     const uint32_t klo = w3_fsr(s.klo, s.khi_prev, W3_SPLIT_MODELS); /* the low word once bit q-3 is in (its top bits are bits of khi_prev either way) */
     const uint32_t rh0 = rh3 >> 1;
