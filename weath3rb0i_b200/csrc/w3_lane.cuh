@@ -464,8 +464,9 @@ W3_HD void w3_pair_init(w3_pair_dec &s, const uint32_t *ab, uint32_t bp0, uint32
  * published -> seen by the coder".  Two guessed bits spread the round trip over three steps
  * (1174 ms for 1 GiB against the pair form's 1331); doing the lookups for both values of the one
  * bit still missing BEFORE it arrives leaves a load, a select and a store on the round trip
- * (1039 ms): the coder warp then waits in one step out of eight and its own ~220 cycles per step
- * are what is left.  Branch-free "attempts" per lane instead of a lockstep wait (the team
+ * (1039 ms; 1013 without a stream prefetch that bought nothing; 952 with W3_SPLIT_FIX = 6): the
+ * coder warp then waits in one step out of eight and its own ~200 cycles per step are what is
+ * left.  Branch-free "attempts" per lane instead of a lockstep wait (the team
  * decoder's coder, w3_team.cuh) were tried too: 160-180 cycles per attempt but 1.5-1.8 attempts
  * per bit, because an attempt that just misses a candidate costs a whole attempt where a poll
  * costs 45 cycles (1193-1292 ms).
