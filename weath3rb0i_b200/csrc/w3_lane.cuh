@@ -487,7 +487,7 @@ struct w3_split_ring {
   uint32_t pub[W3_SPLIT_SLOTS][W3_SPLIT_MAXB][2];
 };
 static_assert(sizeof(w3_split_ring) % 16 == 0, "ring keeps the counters aligned");
-W3_HD uint32_t w3_split_tag(uint32_t q) { return (q + 1u) & 0xFFFFu; } /* never 0: a cleared ring matches nothing */
+W3_HD uint32_t w3_split_tag(uint32_t q) { return (q + 1u) & 0xFFFFu; } /* not 0 before q = 65535: a cleared ring matches nothing, and by then every slot has been written */
 
 /* the coder's step for position q once its candidate word cw is there; cand/pub: the block's columns */
 template <bool kCareful>
