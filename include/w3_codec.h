@@ -205,6 +205,10 @@ int w3_selftest_counter_p(w3_ctx *ctx, uint64_t *mismatches);
  * defines for this path (8 context lookups = 8 sectors per input byte).  No
  * counterpart in the reference. */
 int w3_probe_sector_gather(w3_ctx *ctx, size_t buffer_bytes, double *sectors_per_second);
+/* Measurement support: the name of the decode kernel the launcher takes for n_blocks blocks of block_size bytes
+ * on a device of sm_count SMs under W3_OPT_KERNELS = kernels and W3_OPT_LANE_FORM = lane_form (0, 0 = a fresh
+ * context).  A pure function of its arguments: no device needed. */
+const char *w3_decode_kernel_name(unsigned n_blocks, unsigned block_size, int sm_count, int kernels, int lane_form);
 /* the coder with caller-supplied probabilities — the harness of
  * src/entropy_coding/arithmetic_coder_tests.rs:8-42; `in` is read MSB-first */
 int w3_selftest_ac_encode(w3_ctx *ctx, const uint8_t *in, size_t n_in, const uint16_t *probs,

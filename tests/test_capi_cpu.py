@@ -32,6 +32,22 @@ def test_strerror_and_version(lib):
     assert b"sm_100a" in lib.w3_version()
 
 
+def test_decode_launch_policy(lib):
+    """The launcher's choice of decode kernel by block count (w3_decode_family): teams up to two waves of one
+    CTA per SM, the split form while an SM's blocks fit one CTA of it (8), the pair form beyond; blocks too
+    large for the lane decoders' 32-bit bit counters always go to the teams; options pin a family."""
+    name = lambda nb, bs=1 << 20, k=0, form=0: lib.w3_decode_kernel_name(nb, bs, 148, k, form).decode()
+    assert [name(nb) for nb in (1, 64, 148, 296)] == ["w3_decode_blocks_team"] * 4
+    assert [name(nb) for nb in (297, 512, 1024, 1184)] == ["w3_decode_blocks_split"] * 4
+    assert [name(nb) for nb in (1185, 2048, 4096)] == ["w3_decode_blocks_pair"] * 3
+    assert name(4096, 32 << 20) == "w3_decode_blocks_team"  # auto and forced "many" alike
+    assert name(4096, 32 << 20, 3) == "w3_decode_blocks_team"
+    assert name(1024, k=1) == "w3_decode_blocks_team" and name(1024, k=2) == "w3_decode_blocks_warp"
+    assert name(5, k=3) == "w3_decode_blocks_split" and name(5, k=3, form=2) == "w3_decode_blocks_pair"
+    assert name(4096, k=3, form=4) == "w3_decode_blocks_split" and name(5, k=3, form=1) == "w3_decode_blocks_lane"
+    assert name(5, k=3, form=3) == "w3_decode_blocks_pair"
+
+
 def test_header_parsing(lib):
     ol = C.c_size_t()
     legacy = b"w30i" + (1234).to_bytes(8, "big") + b"\xff"

@@ -23,7 +23,7 @@ SYMBOLS = (
     "w3_ctx_set_model", "w3_ctx_get_model", "w3_train_model", "w3_ctx_set_geometry", "w3_ctx_get_geometry", "w3_sweep",
     "w3_compress", "w3_decompress", "w3_decompress_blocks", "w3_decompressed_size", "w3_cm_compress", "w3_cm_decompress",
     "w3_encode_device", "w3_pack_device", "w3_decode_device",
-    "w3_selftest_achash", "w3_selftest_counter_p", "w3_probe_sector_gather", "w3_selftest_ac_encode", "w3_selftest_ac_decode",
+    "w3_selftest_achash", "w3_selftest_counter_p", "w3_probe_sector_gather", "w3_decode_kernel_name", "w3_selftest_ac_encode", "w3_selftest_ac_decode",
     "w3_selftest_state_table", "w3_selftest_hashslots",
     "w3_strerror", "w3_last_cuda_error", "w3_version",
 )
@@ -82,7 +82,8 @@ def load():
     lib.w3_selftest_ac_decode.argtypes = [vp, u8p, sz, vp, sz, u8p, sz]
     lib.w3_selftest_state_table.argtypes = [vp, C.c_int, vp, vp, vp, sz]
     lib.w3_selftest_hashslots.argtypes = [vp, vp, sz, vp, sz, vp]
-    for f in ("w3_strerror", "w3_last_cuda_error", "w3_version"):
+    lib.w3_decode_kernel_name.argtypes = [C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int]
+    for f in ("w3_strerror", "w3_last_cuda_error", "w3_version", "w3_decode_kernel_name"):
         getattr(lib, f).restype = C.c_char_p
     lib.w3_strerror.argtypes = [C.c_int]
     _lib = lib

@@ -628,6 +628,7 @@ static inline int w3_pick_warps(uint32_t n_blocks, int sm_count) {
  *          (w3_lane.cuh) — an instruction costs the same for 1 or 32 active lanes.
  *   warp   round 1's one-warp-per-block kernels, kept for comparison. */
 enum { W3_K_AUTO = 0, W3_K_TEAM = 1, W3_K_WARP = 2, W3_K_MANY = 3 };
+enum { W3_DEC_TEAM = 1, W3_DEC_WARP = 2, W3_DEC_LANE = 3, W3_DEC_PAIR = 4, W3_DEC_PAIR_P = 5, W3_DEC_SPLIT = 6 }; /* w3_decode_family */
 
 static inline uint32_t w3_ceil_div(uint32_t a, uint32_t b) { return (a + b - 1u) / b; }
 
@@ -740,39 +741,58 @@ cudaError_t w3_launch_scan(const uint32_t *d_lens, uint32_t n_blocks, uint64_t *
   return cudaGetLastError();
 }
 
+/* The decode kernel w3_launch_decode takes for `n_blocks` blocks of `block_size` bytes on a device of `sm_count`
+ * SMs under the options (kernels = W3_OPT_KERNELS, lane_form = W3_OPT_LANE_FORM): the launcher's policy in one
+ * place (bench.py names the dominant kernel of its roofline through w3_decode_kernel_name).
+ *   team   up to two waves of one CTA per block, and for blocks the 32-bit bit counters of the other forms cannot index
+ *   split  beyond, while the blocks of an SM fit one CTA of it (w3_lane.cuh: 1 GiB / 1024 blocks 952 ms against the pair
+ *          form's 1331, profiles/r02_spin_variants.txt, r02_split_fix_variants.txt); its pace does not depend on the number
+ *          of blocks in the CTA, so more than 8 per SM would mean rounds
+ *   pair   beyond that (4096 x 256 KiB: 681 ms against the split form's ~1000, profiles/r02_decode_policy.txt) */
+int w3_decode_family(uint32_t n_blocks, uint32_t block_size, int sm_count, int kernels, int lane_form) {
+  int k = kernels;
+  /* the lane decoders count stream bits in 32 bits: blocks they cannot be sure about go to the team kernel */
+  const bool lane_ok = block_size <= (16u << 20);
+  if (k == W3_K_AUTO) k = (n_blocks > W3_TEAM_MAX_WAVES * (uint32_t)sm_count && lane_ok) ? W3_K_MANY : W3_K_TEAM;
+  if (k == W3_K_MANY && !lane_ok) k = W3_K_TEAM;
+  if (k == W3_K_TEAM) return W3_DEC_TEAM;
+  if (k == W3_K_WARP) return W3_DEC_WARP;
+  const uint32_t q = w3_ceil_div(n_blocks, (uint32_t)sm_count);
+  if (lane_form == 4 || (lane_form == 0 && q <= W3_SPLIT_MAXB)) return W3_DEC_SPLIT;
+  if (lane_form == 1) return W3_DEC_LANE;
+  return lane_form == 3 ? W3_DEC_PAIR_P : W3_DEC_PAIR; /* the probability table measured slower (profiles/r02_pair_variants.txt): on request only */
+}
+const char *w3_decode_kernel_name(uint32_t n_blocks, uint32_t block_size, int sm_count, int kernels, int lane_form) {
+  switch (w3_decode_family(n_blocks, block_size, sm_count, kernels, lane_form)) {
+    case W3_DEC_TEAM: return "w3_decode_blocks_team";
+    case W3_DEC_WARP: return "w3_decode_blocks_warp";
+    case W3_DEC_LANE: return "w3_decode_blocks_lane";
+    case W3_DEC_SPLIT: return "w3_decode_blocks_split";
+    default: return "w3_decode_blocks_pair";
+  }
+}
+
 cudaError_t w3_launch_decode(const uint8_t *d_comp, const uint64_t *d_offsets, uint32_t n_blocks,
                              uint32_t block_size, uint64_t n_total, uint8_t *d_out,
                              uint32_t *d_err, const w3_hashtab *d_tab, int sm_count,
                              const w3_launch_opts *opts, cudaStream_t s) {
   if (!n_blocks) return cudaSuccess;
-  int k = opts ? opts->kernels : W3_K_AUTO;
-  /* the lane decoder counts stream bits in 32 bits: blocks it cannot be sure about go to the team kernel */
-  const bool lane_ok = block_size <= (16u << 20);
-  if (k == W3_K_AUTO) k = (n_blocks > W3_TEAM_MAX_WAVES * (uint32_t)sm_count && lane_ok) ? W3_K_MANY : W3_K_TEAM;
-  if (k == W3_K_MANY && !lane_ok) k = W3_K_TEAM;
-  if (k == W3_K_TEAM) {
+  const int form = opts ? opts->lane_form : 0;
+  const int fam = w3_decode_family(n_blocks, block_size, sm_count, opts ? opts->kernels : W3_K_AUTO, form);
+  if (fam == W3_DEC_TEAM) {
     w3_decode_blocks_team<<<n_blocks, W3_DEC_TEAM_THREADS,
                             sizeof(w3_dec_tab) + sizeof(w3_dec_team), s>>>(
         d_comp, d_offsets, n_blocks, block_size, n_total, d_out, d_err, d_tab);
     return cudaGetLastError();
   }
-  if (k == W3_K_WARP) {
+  if (fam == W3_DEC_WARP) {
     int warps = w3_pick_warps(n_blocks, sm_count);
     uint32_t grid = (n_blocks + (uint32_t)warps - 1) / (uint32_t)warps;
     w3_decode_blocks_warp<<<grid, warps * 32, w3_dense_dec_smem_bytes(warps), s>>>(
         d_comp, d_offsets, n_blocks, block_size, n_total, d_out, d_tab);
     return cudaGetLastError();
   }
-  /* lanes: `resident` blocks per CTA at a time, spread over `warps` warps (one per SM
-   * sub-partition by default) of `lanes` blocks each; the pair form (two lanes per block, the next
-   * position's lookup overlapping the current bit's coder step) unless the lane form is asked for.
-   * Form 3 keeps Counter::p of every counter in a second table (16 KiB per block). */
-  const int form = opts ? opts->lane_form : 0;
-  const uint32_t q = w3_ceil_div(n_blocks, (uint32_t)sm_count);
-  /* Split form (w3_lane.cuh) when the blocks of an SM fit one CTA of it: measured on 1 GiB / 1024 blocks
-   * (profiles/r02_spin_variants.txt) 1039 ms against the pair form's 1331.  Its pace does not depend on the number of
-   * blocks in the CTA, so more than 8 per SM would mean rounds: 4096 x 256 KiB stays with the pair form. */
-  if (form == 4 || (form == 0 && q <= W3_SPLIT_MAXB)) {
+  if (fam == W3_DEC_SPLIT) {
     uint32_t group = w3_per_cta(n_blocks, sm_count, W3_SPLIT_MAXB);
     if (form == 4 && opts && opts->lane_warps > 0) group = (uint32_t)opts->lane_warps < W3_SPLIT_MAXB ? (uint32_t)opts->lane_warps : W3_SPLIT_MAXB;
     uint32_t grid = w3_ceil_div(n_blocks, group);
@@ -781,8 +801,12 @@ cudaError_t w3_launch_decode(const uint8_t *d_comp, const uint64_t *d_offsets, u
         d_comp, d_offsets, n_blocks, block_size, n_total, d_out, d_err, d_tab, group);
     return cudaGetLastError();
   }
-  const bool pair = form != 1;
-  const bool cache_p = pair && form == 3; /* measured slower than recomputing (profiles/r02_pair_variants.txt): on request only */
+  /* lanes: `resident` blocks per CTA at a time, spread over `warps` warps (one per SM
+   * sub-partition by default) of `lanes` blocks each; the pair form (two lanes per block, the next
+   * position's lookup overlapping the current bit's coder step) unless the lane form is asked for.
+   * W3_DEC_PAIR_P keeps Counter::p of every counter in a second table (16 KiB per block). */
+  const bool pair = fam != W3_DEC_LANE;
+  const bool cache_p = fam == W3_DEC_PAIR_P;
   const uint32_t cap = cache_p ? w3_lane_cap() / 2u : w3_lane_cap();
   const uint32_t per = w3_per_cta(n_blocks, sm_count, cap);
   uint32_t warps = per < 4u ? per : 4u;

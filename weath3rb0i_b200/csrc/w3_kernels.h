@@ -37,6 +37,9 @@ cudaError_t w3_launch_decode(const uint8_t *d_comp, const uint64_t *d_offsets, u
                              uint32_t block_size, uint64_t n_total, uint8_t *d_out,
                              uint32_t *d_err, const struct w3_hashtab *d_tab, int sm_count,
                              const struct w3_launch_opts *opts, cudaStream_t s);
+/* the launcher's choice of decode kernel (w3_kernels.cu: W3_DEC_*), and its name */
+int w3_decode_family(uint32_t n_blocks, uint32_t block_size, int sm_count, int kernels, int lane_form);
+const char *w3_decode_kernel_name(uint32_t n_blocks, uint32_t block_size, int sm_count, int kernels, int lane_form);
 /* StationaryModel::new on the device: d_cnt needs ceil(n / 1024) * 8 u16 */
 cudaError_t w3_launch_train(const uint8_t *d_in, uint64_t n, uint16_t *d_cnt, uint16_t *d_table,
                             int sm_count, cudaStream_t s);
